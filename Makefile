@@ -1,0 +1,29 @@
+# Builds the product: libsw4b200.so (CUDA kernels + host engine behind the C ABI) and the drop-in CLIs.
+# sm_100a only; artefacts stay in-tree (git-ignored) so they travel to the GPU box.
+NVCC     ?= nvcc
+CXXHOST  := $(shell command -v /usr/bin/g++ || echo g++)
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := -std=c++17 -O3 -lineinfo $(ARCH) -ccbin $(CXXHOST) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+CSRC     := cudasw4_b200/csrc
+LIB      := cudasw4_b200/libsw4b200.so
+HDRS     := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.hpp) include/sw4b200.h
+
+.PHONY: all lib cli oracle clean
+all: lib cli
+
+lib: $(LIB)
+$(LIB): $(CSRC)/engine.cu $(HDRS)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/engine.cu -lpthread 2> build/engine.ptxas.log || (cat build/engine.ptxas.log; exit 1)
+	@grep -E "error|spill" build/engine.ptxas.log | sort | uniq -c | sort -rn | head -20 || true
+
+cli: build/align build/makedb
+build/align: $(CSRC)/cli_align.cpp include/cudasw4.cuh include/sw4b200.h $(CSRC)/fasta_reader.hpp $(LIB)
+	$(CXXHOST) -std=c++17 -O2 -Wall -Iinclude -o $@ $(CSRC)/cli_align.cpp -Lcudasw4_b200 -lsw4b200 -Wl,-rpath,'$$ORIGIN/../cudasw4_b200' -lz
+build/makedb: $(CSRC)/cli_makedb.cpp $(CSRC)/fasta_reader.hpp
+	$(CXXHOST) -std=c++17 -O2 -Wall -o $@ $(CSRC)/cli_makedb.cpp -lz
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -f $(LIB) build/align build/makedb build/*.log

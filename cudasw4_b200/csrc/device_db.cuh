@@ -1,0 +1,67 @@
+// Device-resident database layout + per-query preparation kernels.
+//
+// Replaces the reference's GpuDatabaseAllocation / batch copy plans (src/gpudatabaseallocation.cuh:22-61,
+// src/dbbatching.cuh:16-99) and the per-block LUT expansion + query staging (src/dpx_s16_kernels.cuh:55-69,
+// src/cudasw4.cuh:1280-1310):
+//   * raw shard      chars / offsets / lengths exactly as makedb stores them (used by the exact 32-bit kernel)
+//   * pair-blocks    for every length class (G lanes x R columns): consecutive subjects of the length-sorted shard are
+//                    paired, and column c of the pair is stored as the fused code f = s0[c] + 21*s1[c] (u16), padded
+//                    with the 'other' code 20; one block = G*R*2 contiguous bytes = one coalesced cp.async burst
+//   * query profile  prof[f][p] = (M[q_p][s1] << 16) | (M[q_p][s0] & 0xffff) for every query position p, built once per
+//                    scan (441 x q words); positions >= q hold -16000 ("gap rows" of the kernel's schedule)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sw4 {
+
+// letters -> residue codes (reference src/convert.cuh:6-34): the 20 upper-case letters in NCBI order, all else 20
+__global__ void convert_query_kernel(const char* __restrict__ letters, uint8_t* __restrict__ codes, int n, int padTo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= padTo) return;
+    uint8_t c = 20;
+    if (i < n) {
+        const char a = letters[i];
+        const char order[21] = "ARNDCQEGHILKMFPSTWYV";
+#pragma unroll
+        for (int k = 0; k < 20; k++)
+            if (a == order[k]) c = (uint8_t)k;
+    }
+    codes[i] = c;
+}
+
+__global__ void build_profile_kernel(const uint8_t* __restrict__ qcodes, int qlen, const int8_t* __restrict__ matrix,
+                                     uint32_t* __restrict__ profile, int stride) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;  // fused pair: s0 = f % 21 (low half), s1 = f / 21 (high half)
+    if (p >= stride) return;
+    uint32_t v = 0xc180c180u;  // (-16000, -16000)
+    if (p < qlen) {
+        const int qc = qcodes[p];
+        const int lo = matrix[qc * 21 + f % 21], hi = matrix[qc * 21 + f / 21];
+        v = ((uint32_t)(uint16_t)(int16_t)hi << 16) | (uint16_t)(int16_t)lo;
+    }
+    profile[(size_t)f * stride + p] = v;
+}
+
+// One thread per (pair-block, column). Subjects [first, first+count) of the shard (ascending length) form blocks
+// b = 0..ceil(count/2)-1 with members first+2b (low half) and first+2b+1 (high half, absent for an odd tail).
+__global__ void build_pair_blocks_kernel(const uint8_t* __restrict__ chars, const size_t* __restrict__ offsets,
+                                         const int32_t* __restrict__ lengths, int first, int count, int columns,
+                                         uint16_t* __restrict__ cols, int2* __restrict__ pairSubjects) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int numBlocks = (count + 1) / 2;
+    const long long total = (long long)numBlocks * columns;
+    if (gid >= total) return;
+    const int b = (int)(gid / columns), c = (int)(gid % columns);
+    const int s0 = first + 2 * b, s1 = s0 + 1;
+    const bool has1 = (2 * b + 1) < count;
+    int r0 = 20, r1 = 20;
+    if (c < lengths[s0]) r0 = chars[offsets[s0] + c];
+    if (has1 && c < lengths[s1]) r1 = chars[offsets[s1] + c];
+    r0 = min(r0, 20); r1 = min(r1, 20);
+    cols[gid] = (uint16_t)(r0 + 21 * r1);
+    if (c == 0) pairSubjects[b] = make_int2(s0, has1 ? s1 : -1);
+}
+
+}  // namespace sw4

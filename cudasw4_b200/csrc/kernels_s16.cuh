@@ -1,0 +1,254 @@
+// Inter-sequence Gotoh score kernel, packed s16x2 (two subjects per lane), for subjects that fit one register tile.
+//
+// Replaces the reference's NW_local_affine_single_pass_dpx_s16 family (src/dpx_s16_kernels.cuh:764-1055, 1220-1357)
+// with a different organisation, designed around what the B200 SM measures (tools/ubench/pipes.cu, profiles/):
+// DPX min/max ops issue on the ALU pipe at 2 warp-inst/clk/SM, VIADD.16x2 on the FMA pipe at 2/clk/SM, issue is
+// 4/clk/SM and shared memory serves one conflict-free 32-lane request per clock. The recurrence needs 3.5 ALU-pipe
+// ops + 2 VIADD + 1 substitution fetch per cell-pair, so everything else must cost ~0:
+//
+//  * Warp = one 32-stage systolic pipeline (lane l works on query row t-l at step t), cut into 32/G independent
+//    groups of G lanes; each group aligns one *pair-block* (two subjects, G*R columns, R register columns per lane)
+//    and groups restart back-to-back on their own schedule (period P = q+G-1 rounded to 4), so there is no
+//    warp-wide fill/drain.
+//  * Substitution scores come from a *positional* query profile: prof[f][p] = (M[q_p][s1] << 16 | M[q_p][s0]) for the
+//    fused residue pair f = s0 + 21*s1. A 64-step sliding window of it lives in shared memory as ring[f][96]
+//    (64 slots + 32 mirrored), refilled with cp.async 16 steps ahead. Lane l reads slot (t-l): the 32 lanes of a warp
+//    always hit 32 different banks (no conflicts, whatever the residues are), and the address is
+//    (per-column register, fixed for the whole alignment) + (warp-uniform step offset): no per-cell address math.
+//  * The device database stores pair-blocks as the fused u16 column codes (cudasw4_b200/csrc/device_db.cuh), fetched
+//    one block ahead with cp.async into a per-group staging area.
+//
+// Arithmetic (bit-exact vs the oracle): H = max(0, diag+s, E, F); t = H+gop; E' = max(E+gex, t); F' = max(F+gex, t);
+// packed modular s16 adds, -16000 as minus infinity; a pair whose running maximum reaches `ovfThreshold` is
+// re-scored in 32 bit (kernels_s32.cuh), exactly the reference's envelope argument.
+#pragma once
+#include <cstdint>
+#include <utility>
+#include <cuda_runtime.h>
+
+namespace sw4 {
+
+constexpr int kS16Threads = 512;           // 16 warps, one CTA per SM
+constexpr int kS16Warps = kS16Threads / 32;
+constexpr int kRingSlots = 64;
+constexpr int kRingStride = 96;            // words per fused-pair row: 32 mirrored + 64 live slots
+constexpr int kFused = 441;                // 21 x 21 residue pairs
+constexpr int kFillBatch = 16;             // steps between ring refills / CTA barriers
+constexpr int kRingBytes = kFused * kRingStride * 4;
+constexpr short kNegS16 = -16000;
+
+struct S16Params {
+    const uint16_t* cols;        // [numBlocks][G*R] fused column codes, lane-major (lane m owns [m*R, m*R+R))
+    const int2* pairSubjects;    // [numBlocks] local subject index of the low / high half (-1 = none)
+    int numBlocks;
+    int logG;                    // G = 1 << logG lanes per group
+    const uint32_t* profile;     // [441][profStride] positional query profile
+    int profStride;
+    int qlen;
+    int period;                  // P: steps between two alignments of a group; multiple of 4, >= max(32, qlen + G - 1)
+    uint32_t gop2, gex2;         // gap scores replicated in both halves
+    int ovfThreshold;            // running maximum >= this => exact 32-bit re-scoring (25000, reference MAX_ACC_SHORT)
+    int statThreshold;           // running maximum >= this => counted in stats.num_overflows (25000, or 2048 for Half2)
+    int32_t* scores;             // [numLocalSubjects]
+    int32_t* ovfList;            // local subject indices that need the exact 32-bit path
+    int* ovfCount;
+    int* statCount;
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <int N, class Fn, int... Is>
+__device__ __forceinline__ void static_for_impl(Fn&& fn, std::integer_sequence<int, Is...>) {
+    (fn(std::integral_constant<int, Is>{}), ...);
+}
+// compile-time unrolled loop: fn(std::integral_constant<int, i>) for i in [0, N)
+template <int N, class Fn>
+__device__ __forceinline__ void static_for(Fn&& fn) {
+    static_for_impl<N>(fn, std::make_integer_sequence<int, N>{});
+}
+
+template <int IMM>
+__device__ __forceinline__ uint32_t lds_u32_imm(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int R>
+constexpr int s16_smem_bytes() { return kRingBytes + kS16Warps * 32 * R * 2; }
+
+// Refill ring slots for global steps [x0, x0+16) (x0 % 16 == 0); p0 = x0 mod period.
+__device__ __forceinline__ void ring_fill(uint32_t ringBase, const uint32_t* __restrict__ profile, int profStride, int x0,
+                                          int p0, int period) {
+    const int slot0 = x0 & (kRingSlots - 1);
+    for (int id = threadIdx.x; id < kFused * (kFillBatch / 4); id += kS16Threads) {
+        const int f = id >> 2, c = id & 3;
+        int p = p0 + 4 * c;
+        if (p >= period) p -= period;
+        if (p >= period) p -= period;  // period can be < 16 only for degenerate queries; be safe
+        const int slot = slot0 + 4 * c;
+        const uint32_t* src = profile + (size_t)f * profStride + p;
+        const uint32_t dst = ringBase + (f * kRingStride + 32 + slot) * 4;
+        cp_async16(dst, src);
+        if (slot >= 32) cp_async16(dst - kRingSlots * 4, src);
+    }
+    cp_async_commit();
+}
+
+template <int R>
+__global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params prm) {
+    static_assert(R % 8 == 0, "R must be a multiple of 8 (16-byte staging chunks per lane)");
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t ringBase = (uint32_t)__cvta_generic_to_shared(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int logG = prm.logG, G = 1 << logG;
+    const int g = lane >> logG, m = lane & (G - 1);
+    const int groupsPerWarp = 32 >> logG;
+    const int totalGroups = gridDim.x * kS16Warps * groupsPerWarp;
+    const int P = prm.period;
+    const int rounds = (prm.numBlocks + totalGroups - 1) / totalGroups;
+    const unsigned groupMask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (g << logG));
+
+    // this group's staging area (G*R fused u16 column codes of the next pair-block), this lane's R*2 bytes of it
+    const uint32_t stageLane =
+        ringBase + kRingBytes + (warp * 32 + lane) * (R * 2);
+
+    uint32_t colAddr[R];  // ring byte address of this column's fused-pair row (lane and batch-phase offsets folded in)
+    uint32_t Hp[R];       // H of the previous row
+    uint32_t F[R];        // F for the next row
+    const uint32_t NEG2 = ((uint32_t)(uint16_t)kNegS16 << 16) | (uint16_t)kNegS16;
+    uint32_t mx = 0, Elast = NEG2, HinPrev = 0;
+#pragma unroll
+    for (int j = 0; j < R; j++) { colAddr[j] = ringBase; Hp[j] = 0; F[j] = NEG2; }
+    // p = this lane's row in the period-P schedule, (t - lane) mod P. The group restarts (stores the finished pair,
+    // loads the next one) when its first lane is at row 0, i.e. when this lane is at row pRestart.
+    int p = (lane == 0) ? 0 : P - lane;
+    const int pRestart = (m == 0) ? 0 : P - m;
+    int nextBlk = (blockIdx.x * kS16Warps + warp) * groupsPerWarp + g;  // block index of the NEXT alignment
+    bool haveWork = false;
+
+    auto prefetch_block = [&](int blk) {  // the G lanes of a group copy G*R*2 bytes: R*2/16 chunks per lane
+        if (blk < prm.numBlocks) {
+            const unsigned char* src = (const unsigned char*)(prm.cols + (size_t)blk * (G * R)) + m * (R * 2);
+#pragma unroll
+            for (int i = 0; i < R * 2 / 16; i++) cp_async16(stageLane + i * 16, src + i * 16);
+        }
+        cp_async_commit();
+    };
+
+    // prologue: lanes l > 0 run their first l steps at "negative time" (rows before the query starts): those ring
+    // slots must read as gap rows too, so the whole ring starts out as -16000; then the first batch + first pair-block.
+    for (int i = threadIdx.x; i < kFused * kRingStride; i += kS16Threads) reinterpret_cast<uint32_t*>(smem)[i] = NEG2;
+    __syncthreads();
+    ring_fill(ringBase, prm.profile, prm.profStride, 0, 0, P);
+    prefetch_block(nextBlk);
+    int pfill = kFillBatch % P;  // (next fill start) mod P
+
+    // The step offset inside the ring is an instruction immediate: 16 steps are unrolled and the column addresses are
+    // advanced by 64 bytes once per batch (ptxas does not fold a uniform register into LDS addresses, and an
+    // address add per cell would cost an issue slot per cell-pair).
+    uint32_t phaseBase = ringBase + (32 - lane) * 4;  // + 64 bytes per batch, wrapping every 4 batches
+    const int numBatches = (rounds * P + 32 + kFillBatch - 1) / kFillBatch;
+#pragma unroll 1
+    for (int batch = 0; batch < numBatches; ++batch) {
+        cp_async_wait_all();
+        __syncthreads();
+        ring_fill(ringBase, prm.profile, prm.profStride, (batch + 1) * kFillBatch, pfill, P);
+        pfill += kFillBatch;
+        while (pfill >= P) pfill -= P;
+        if (batch > 0) {
+            const int delta = (batch & 3) ? kFillBatch * 4 : -(kRingSlots - kFillBatch) * 4;
+            phaseBase += delta;
+#pragma unroll
+            for (int j = 0; j < R; j++) colAddr[j] += delta;
+        }
+        static_for<kFillBatch>([&](auto stepIndex) {
+            constexpr int i = decltype(stepIndex)::value;
+            if ((i & 3) == 0 && p == pRestart) {  // group restart: uniform within the group, divergent across groups
+                if (haveWork) {
+                    uint32_t r = mx;
+                    for (int o = G >> 1; o > 0; o >>= 1) r = __vmaxs2(r, __shfl_xor_sync(groupMask, r, o));
+                    if (m == 0) {
+                        const int2 subj = prm.pairSubjects[nextBlk - totalGroups];
+                        const int lo = (int)(short)(r & 0xffff), hi = (int)(short)(r >> 16);
+                        if (subj.x >= 0) {
+                            if (lo >= prm.statThreshold) atomicAdd(prm.statCount, 1);
+                            if (lo >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = subj.x;
+                            prm.scores[subj.x] = lo;
+                        }
+                        if (subj.y >= 0) {
+                            if (hi >= prm.statThreshold) atomicAdd(prm.statCount, 1);
+                            if (hi >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = subj.y;
+                            prm.scores[subj.y] = hi;
+                        }
+                    }
+                }
+                haveWork = nextBlk < prm.numBlocks;
+                if (haveWork) {
+                    cp_async_wait_all();
+                    __syncwarp(groupMask);
+#pragma unroll
+                    for (int b = 0; b < R / 8; b++) {
+                        uint32_t w0, w1, w2, w3;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(stageLane + b * 16));
+                        const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            colAddr[b * 8 + e * 2 + 0] = phaseBase + (w[e] & 0xffffu) * (kRingStride * 4);
+                            colAddr[b * 8 + e * 2 + 1] = phaseBase + (w[e] >> 16) * (kRingStride * 4);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < R; j++) { Hp[j] = 0; F[j] = NEG2; }
+                    mx = 0; HinPrev = 0;
+                    __syncwarp(groupMask);
+                    prefetch_block(nextBlk + totalGroups);
+                }
+                nextBlk += totalGroups;
+            }
+            // systolic hand-over from the previous lane (row p was computed there one step earlier)
+            uint32_t Hin = __shfl_up_sync(0xffffffffu, Hp[R - 1], 1);
+            uint32_t Ein = __shfl_up_sync(0xffffffffu, Elast, 1);
+            // Rows p >= q are "gap rows" between two alignments of the group: they are computed like any other row (no
+            // branch => no register shuffling at a merge point) on profile entries of -16000, with the hand-over
+            // inputs forced to the boundary values so that nothing leaks into the freshly reset state; they can
+            // never raise the running maximum.
+            if (m == 0 || (unsigned)p >= (unsigned)prm.qlen) { Hin = 0; Ein = NEG2; }
+            {
+                uint32_t E = Ein;
+                uint32_t d = __vadd2(HinPrev, lds_u32_imm<i * 4>(colAddr[0]));
+                uint32_t dPrev = 0;
+#pragma unroll
+                for (int j = 0; j < R; j++) {
+                    // look-ahead: the next column's diagonal term reads Hp[j] before this column overwrites it
+                    uint32_t dNext = 0;
+                    if (j + 1 < R) dNext = __vadd2(Hp[j], lds_u32_imm<i * 4>(colAddr[j + 1]));
+                    const uint32_t h = __vimax3_s16x2_relu(d, E, F[j]);
+                    Hp[j] = h;
+                    const uint32_t tt = __vadd2(h, prm.gop2);
+                    E = __viaddmax_s16x2(E, prm.gex2, tt);
+                    F[j] = __viaddmax_s16x2(F[j], prm.gex2, tt);
+                    // max over d == max over H: a best local alignment ends on a match, and d having a second use
+                    // keeps ptxas from fusing the add into an ALU-pipe VIADDMNMX
+                    if (j & 1) mx = __vimax3_s16x2(mx, d, dPrev);
+                    dPrev = d;
+                    d = dNext;
+                }
+                Elast = E;
+                HinPrev = Hin;
+            }
+            if (++p == P) p = 0;
+        });
+    }
+}
+
+}  // namespace sw4
