@@ -62,10 +62,11 @@ struct Error {
 // ---------------------------------------------------------------------------------------------------------------
 // length classes of the packed 16-bit kernel: G lanes x R columns, capacity G*R
 // ---------------------------------------------------------------------------------------------------------------
-struct LengthClass { int logG, R, capacity; };
+struct LengthClass { int logG, R, NA, capacity; };  // G = 1<<logG lanes x R columns, NA pair-blocks interleaved per lane
 static const LengthClass kLengthClasses[] = {
-    {2, 8, 32},   {2, 16, 64},  {2, 24, 96},   {2, 32, 128},  {3, 24, 192},
-    {3, 32, 256}, {4, 24, 384}, {4, 32, 512},  {5, 24, 768},  {5, 32, 1024},
+    {2, 8, 1, 32},    {2, 16, 1, 64},   {2, 24, 1, 96},   {2, 32, 1, 128},  {3, 20, 1, 160},  {3, 24, 1, 192},
+    {3, 28, 1, 224},  {3, 32, 1, 256},  {4, 20, 1, 320},  {4, 24, 1, 384},  {4, 28, 1, 448},  {4, 32, 1, 512},
+    {5, 20, 1, 640},  {5, 24, 1, 768},  {5, 28, 1, 896},  {5, 32, 1, 1024},
 };
 constexpr int kNumLengthClasses = sizeof(kLengthClasses) / sizeof(kLengthClasses[0]);
 constexpr int kMaxS16Length = 1024;
@@ -204,16 +205,16 @@ struct Shard {
     }
 };
 
-template <int R>
+template <int R, int NA>
 static void launch_s16(const S16Params& prm, int grid, cudaStream_t stream) {
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        SW4_CUDA(cudaFuncSetAttribute(sw_s16_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16_smem_bytes<R>()));
+        SW4_CUDA(cudaFuncSetAttribute(sw_s16_kernel<R, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16_smem_bytes<R, NA>()));
         configured[dev & 63] = true;
     }
-    sw_s16_kernel<R><<<grid, kS16Threads, s16_smem_bytes<R>(), stream>>>(prm);
+    sw_s16_kernel<R, NA><<<grid, kS16Threads, s16_smem_bytes<R, NA>(), stream>>>(prm);
     SW4_CUDA(cudaGetLastError());
 }
 
@@ -451,13 +452,17 @@ struct Engine {
             prm.ovfCount = sh.dCounters.p + 0;
             prm.statCount = sh.dCounters.p + 1;
             const int groupsPerCta = kS16Warps * (32 >> lc.logG);
-            const int grid = std::max(1, std::min(sh.smCount, (cl.numBlocks + groupsPerCta - 1) / groupsPerCta));
-            switch (lc.R) {
-                case 8: launch_s16<8>(prm, grid, st); break;
-                case 16: launch_s16<16>(prm, grid, st); break;
-                case 24: launch_s16<24>(prm, grid, st); break;
-                case 32: launch_s16<32>(prm, grid, st); break;
-                default: fail(SW4_ERR_INVALID, "no kernel for R=%d", lc.R);
+            const int superBlocks = (cl.numBlocks + lc.NA - 1) / lc.NA;
+            const int grid = std::max(1, std::min(sh.smCount, (superBlocks + groupsPerCta - 1) / groupsPerCta));
+            const int key = lc.R * 10 + lc.NA;
+            switch (key) {
+                case 81: launch_s16<8, 1>(prm, grid, st); break;
+                case 161: launch_s16<16, 1>(prm, grid, st); break;
+                case 201: launch_s16<20, 1>(prm, grid, st); break;
+                case 241: launch_s16<24, 1>(prm, grid, st); break;
+                case 281: launch_s16<28, 1>(prm, grid, st); break;
+                case 321: launch_s16<32, 1>(prm, grid, st); break;
+                default: fail(SW4_ERR_INVALID, "no kernel for R=%d NA=%d", lc.R, lc.NA);
             }
             sh.launches++;
         }

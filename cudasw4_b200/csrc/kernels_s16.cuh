@@ -79,11 +79,14 @@ __device__ __forceinline__ uint32_t lds_u32_imm(uint32_t addr) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
 }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int R>
-constexpr int s16_smem_bytes() { return kRingBytes + kS16Warps * 32 * R * 2; }
+template <int R, int NA>
+constexpr int s16_smem_bytes() { return kRingBytes + kS16Warps * 32 * NA * R * 2; }
 
 // Refill ring slots for global steps [x0, x0+16) (x0 % 16 == 0); p0 = x0 mod period.
 __device__ __forceinline__ void ring_fill(uint32_t ringBase, const uint32_t* __restrict__ profile, int profStride, int x0,
@@ -93,7 +96,7 @@ __device__ __forceinline__ void ring_fill(uint32_t ringBase, const uint32_t* __r
         const int f = id >> 2, c = id & 3;
         int p = p0 + 4 * c;
         if (p >= period) p -= period;
-        if (p >= period) p -= period;  // period can be < 16 only for degenerate queries; be safe
+        if (p >= period) p -= period;
         const int slot = slot0 + 4 * c;
         const uint32_t* src = profile + (size_t)f * profStride + p;
         const uint32_t dst = ringBase + (f * kRingStride + 32 + slot) * 4;
@@ -103,9 +106,11 @@ __device__ __forceinline__ void ring_fill(uint32_t ringBase, const uint32_t* __r
     cp_async_commit();
 }
 
-template <int R>
+// R  = register columns per alignment per lane, NA = alignments (pair-blocks) interleaved per lane. NA = 2 gives every
+// warp two independent E/H dependency chains, which is what lets 4 warps per scheduler keep the ALU pipe busy.
+template <int R, int NA>
 __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params prm) {
-    static_assert(R % 8 == 0, "R must be a multiple of 8 (16-byte staging chunks per lane)");
+    static_assert(R % 4 == 0, "a lane's staging slice (R u16 codes) must be a whole number of 8-byte chunks");
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t ringBase = (uint32_t)__cvta_generic_to_shared(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -114,42 +119,55 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
     const int groupsPerWarp = 32 >> logG;
     const int totalGroups = gridDim.x * kS16Warps * groupsPerWarp;
     const int P = prm.period;
-    const int rounds = (prm.numBlocks + totalGroups - 1) / totalGroups;
+    const int superBlocks = (prm.numBlocks + NA - 1) / NA;  // a group aligns NA consecutive pair-blocks at a time
+    const int rounds = (superBlocks + totalGroups - 1) / totalGroups;
     const unsigned groupMask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (g << logG));
 
-    // this group's staging area (G*R fused u16 column codes of the next pair-block), this lane's R*2 bytes of it
-    const uint32_t stageLane =
-        ringBase + kRingBytes + (warp * 32 + lane) * (R * 2);
+    // this lane's slice of the group's staging area: NA x R fused u16 column codes of the next pair-blocks
+    const uint32_t stageLane = ringBase + kRingBytes + (warp * 32 + lane) * (NA * R * 2);
 
-    uint32_t colAddr[R];  // ring byte address of this column's fused-pair row (lane and batch-phase offsets folded in)
-    uint32_t Hp[R];       // H of the previous row
-    uint32_t F[R];        // F for the next row
+    uint32_t colAddr[NA][R];  // ring byte address of this column's fused-pair row (lane and batch-phase offsets folded in)
+    uint32_t Hp[NA][R];       // H of the previous row
+    uint32_t F[NA][R];        // F for the next row
     const uint32_t NEG2 = ((uint32_t)(uint16_t)kNegS16 << 16) | (uint16_t)kNegS16;
-    uint32_t mx = 0, Elast = NEG2, HinPrev = 0;
+    uint32_t mx[NA], Elast[NA], HinPrev[NA];
 #pragma unroll
-    for (int j = 0; j < R; j++) { colAddr[j] = ringBase; Hp[j] = 0; F[j] = NEG2; }
-    // p = this lane's row in the period-P schedule, (t - lane) mod P. The group restarts (stores the finished pair,
-    // loads the next one) when its first lane is at row 0, i.e. when this lane is at row pRestart.
+    for (int a = 0; a < NA; a++) {
+        mx[a] = 0; Elast[a] = NEG2; HinPrev[a] = 0;
+#pragma unroll
+        for (int j = 0; j < R; j++) { colAddr[a][j] = ringBase; Hp[a][j] = 0; F[a][j] = NEG2; }
+    }
+    // p = this lane's row in the period-P schedule, (t - lane) mod P. The group restarts (stores the finished pairs,
+    // loads the next ones) when its first lane is at row 0, i.e. when this lane is at row pRestart.
     int p = (lane == 0) ? 0 : P - lane;
     const int pRestart = (m == 0) ? 0 : P - m;
-    int nextBlk = (blockIdx.x * kS16Warps + warp) * groupsPerWarp + g;  // block index of the NEXT alignment
+    int nextSuper = (blockIdx.x * kS16Warps + warp) * groupsPerWarp + g;  // super-block index of the NEXT alignments
     bool haveWork = false;
 
-    auto prefetch_block = [&](int blk) {  // the G lanes of a group copy G*R*2 bytes: R*2/16 chunks per lane
-        if (blk < prm.numBlocks) {
-            const unsigned char* src = (const unsigned char*)(prm.cols + (size_t)blk * (G * R)) + m * (R * 2);
+    auto prefetch_blocks = [&](int super) {  // lane m copies its R columns of each of the NA blocks
 #pragma unroll
-            for (int i = 0; i < R * 2 / 16; i++) cp_async16(stageLane + i * 16, src + i * 16);
+        for (int a = 0; a < NA; a++) {
+            const int blk = super * NA + a;
+            if (super < superBlocks && blk < prm.numBlocks) {
+                const unsigned char* src = (const unsigned char*)(prm.cols + (size_t)blk * (G * R)) + m * (R * 2);
+                if constexpr ((R * 2) % 16 == 0) {
+#pragma unroll
+                    for (int i = 0; i < R * 2 / 16; i++) cp_async16(stageLane + a * R * 2 + i * 16, src + i * 16);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < R * 2 / 8; i++) cp_async8(stageLane + a * R * 2 + i * 8, src + i * 8);
+                }
+            }
         }
         cp_async_commit();
     };
 
     // prologue: lanes l > 0 run their first l steps at "negative time" (rows before the query starts): those ring
-    // slots must read as gap rows too, so the whole ring starts out as -16000; then the first batch + first pair-block.
+    // slots must read as gap rows too, so the whole ring starts out as -16000; then the first batch + first pair-blocks.
     for (int i = threadIdx.x; i < kFused * kRingStride; i += kS16Threads) reinterpret_cast<uint32_t*>(smem)[i] = NEG2;
     __syncthreads();
     ring_fill(ringBase, prm.profile, prm.profStride, 0, 0, P);
-    prefetch_block(nextBlk);
+    prefetch_blocks(nextSuper);
     int pfill = kFillBatch % P;  // (next fill start) mod P
 
     // The step offset inside the ring is an instruction immediate: 16 steps are unrolled and the column addresses are
@@ -168,84 +186,94 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
             const int delta = (batch & 3) ? kFillBatch * 4 : -(kRingSlots - kFillBatch) * 4;
             phaseBase += delta;
 #pragma unroll
-            for (int j = 0; j < R; j++) colAddr[j] += delta;
+            for (int a = 0; a < NA; a++)
+#pragma unroll
+                for (int j = 0; j < R; j++) colAddr[a][j] += delta;
         }
         static_for<kFillBatch>([&](auto stepIndex) {
             constexpr int i = decltype(stepIndex)::value;
             if ((i & 3) == 0 && p == pRestart) {  // group restart: uniform within the group, divergent across groups
                 if (haveWork) {
-                    uint32_t r = mx;
-                    for (int o = G >> 1; o > 0; o >>= 1) r = __vmaxs2(r, __shfl_xor_sync(groupMask, r, o));
-                    if (m == 0) {
-                        const int2 subj = prm.pairSubjects[nextBlk - totalGroups];
-                        const int lo = (int)(short)(r & 0xffff), hi = (int)(short)(r >> 16);
-                        if (subj.x >= 0) {
-                            if (lo >= prm.statThreshold) atomicAdd(prm.statCount, 1);
-                            if (lo >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = subj.x;
-                            prm.scores[subj.x] = lo;
-                        }
-                        if (subj.y >= 0) {
-                            if (hi >= prm.statThreshold) atomicAdd(prm.statCount, 1);
-                            if (hi >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = subj.y;
-                            prm.scores[subj.y] = hi;
+#pragma unroll
+                    for (int a = 0; a < NA; a++) {
+                        uint32_t r = mx[a];
+                        for (int o = G >> 1; o > 0; o >>= 1) r = __vmaxs2(r, __shfl_xor_sync(groupMask, r, o));
+                        const int blk = (nextSuper - totalGroups) * NA + a;
+                        if (m == 0 && blk < prm.numBlocks) {
+                            const int2 subj = prm.pairSubjects[blk];
+                            const int lo = (int)(short)(r & 0xffff), hi = (int)(short)(r >> 16);
+                            if (subj.x >= 0) {
+                                if (lo >= prm.statThreshold) atomicAdd(prm.statCount, 1);
+                                if (lo >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = subj.x;
+                                prm.scores[subj.x] = lo;
+                            }
+                            if (subj.y >= 0) {
+                                if (hi >= prm.statThreshold) atomicAdd(prm.statCount, 1);
+                                if (hi >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = subj.y;
+                                prm.scores[subj.y] = hi;
+                            }
                         }
                     }
                 }
-                haveWork = nextBlk < prm.numBlocks;
+                haveWork = nextSuper < superBlocks;
                 if (haveWork) {
                     cp_async_wait_all();
                     __syncwarp(groupMask);
 #pragma unroll
-                    for (int b = 0; b < R / 8; b++) {
-                        uint32_t w0, w1, w2, w3;
-                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(stageLane + b * 16));
-                        const uint32_t w[4] = {w0, w1, w2, w3};
+                    for (int a = 0; a < NA; a++) {
 #pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            colAddr[b * 8 + e * 2 + 0] = phaseBase + (w[e] & 0xffffu) * (kRingStride * 4);
-                            colAddr[b * 8 + e * 2 + 1] = phaseBase + (w[e] >> 16) * (kRingStride * 4);
+                        for (int b = 0; b < R / 2; b++) {
+                            const uint32_t w = lds_u32_imm<0>(stageLane + (a * R + b * 2) * 2);
+                            colAddr[a][b * 2 + 0] = phaseBase + (w & 0xffffu) * (kRingStride * 4);
+                            colAddr[a][b * 2 + 1] = phaseBase + (w >> 16) * (kRingStride * 4);
                         }
-                    }
 #pragma unroll
-                    for (int j = 0; j < R; j++) { Hp[j] = 0; F[j] = NEG2; }
-                    mx = 0; HinPrev = 0;
+                        for (int j = 0; j < R; j++) { Hp[a][j] = 0; F[a][j] = NEG2; }
+                        mx[a] = 0; HinPrev[a] = 0;
+                    }
                     __syncwarp(groupMask);
-                    prefetch_block(nextBlk + totalGroups);
+                    prefetch_blocks(nextSuper + totalGroups);
                 }
-                nextBlk += totalGroups;
+                nextSuper += totalGroups;
             }
-            // systolic hand-over from the previous lane (row p was computed there one step earlier)
-            uint32_t Hin = __shfl_up_sync(0xffffffffu, Hp[R - 1], 1);
-            uint32_t Ein = __shfl_up_sync(0xffffffffu, Elast, 1);
             // Rows p >= q are "gap rows" between two alignments of the group: they are computed like any other row (no
             // branch => no register shuffling at a merge point) on profile entries of -16000, with the hand-over
             // inputs forced to the boundary values so that nothing leaks into the freshly reset state; they can
             // never raise the running maximum.
-            if (m == 0 || (unsigned)p >= (unsigned)prm.qlen) { Hin = 0; Ein = NEG2; }
-            {
-                uint32_t E = Ein;
-                uint32_t d = __vadd2(HinPrev, lds_u32_imm<i * 4>(colAddr[0]));
-                uint32_t dPrev = 0;
+            const bool boundary = (m == 0) || ((unsigned)p >= (unsigned)prm.qlen);
+            uint32_t E[NA], d[NA], dPrev[NA];
 #pragma unroll
-                for (int j = 0; j < R; j++) {
+            for (int a = 0; a < NA; a++) {
+                // systolic hand-over from the previous lane (row p was computed there one step earlier)
+                uint32_t Hin = __shfl_up_sync(0xffffffffu, Hp[a][R - 1], 1);
+                uint32_t Ein = __shfl_up_sync(0xffffffffu, Elast[a], 1);
+                if (boundary) { Hin = 0; Ein = NEG2; }
+                E[a] = Ein;
+                d[a] = __vadd2(HinPrev[a], lds_u32_imm<i * 4>(colAddr[a][0]));
+                dPrev[a] = 0;
+                HinPrev[a] = Hin;
+            }
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+#pragma unroll
+                for (int a = 0; a < NA; a++) {
                     // look-ahead: the next column's diagonal term reads Hp[j] before this column overwrites it
                     uint32_t dNext = 0;
-                    if (j + 1 < R) dNext = __vadd2(Hp[j], lds_u32_imm<i * 4>(colAddr[j + 1]));
-                    const uint32_t h = __vimax3_s16x2_relu(d, E, F[j]);
-                    Hp[j] = h;
+                    if (j + 1 < R) dNext = __vadd2(Hp[a][j], lds_u32_imm<i * 4>(colAddr[a][j + 1]));
+                    const uint32_t h = __vimax3_s16x2_relu(d[a], E[a], F[a][j]);
+                    Hp[a][j] = h;
                     const uint32_t tt = __vadd2(h, prm.gop2);
-                    E = __viaddmax_s16x2(E, prm.gex2, tt);
-                    F[j] = __viaddmax_s16x2(F[j], prm.gex2, tt);
+                    E[a] = __viaddmax_s16x2(E[a], prm.gex2, tt);
+                    F[a][j] = __viaddmax_s16x2(F[a][j], prm.gex2, tt);
                     // max over d == max over H: a best local alignment ends on a match, and d having a second use
                     // keeps ptxas from fusing the add into an ALU-pipe VIADDMNMX
-                    if (j & 1) mx = __vimax3_s16x2(mx, d, dPrev);
-                    dPrev = d;
-                    d = dNext;
+                    if (j & 1) mx[a] = __vimax3_s16x2(mx[a], d[a], dPrev[a]);
+                    dPrev[a] = d[a];
+                    d[a] = dNext;
                 }
-                Elast = E;
-                HinPrev = Hin;
             }
+#pragma unroll
+            for (int a = 0; a < NA; a++) Elast[a] = E[a];
             if (++p == P) p = 0;
         });
     }
