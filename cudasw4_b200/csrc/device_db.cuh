@@ -44,24 +44,25 @@ __global__ void build_profile_kernel(const uint8_t* __restrict__ qcodes, int qle
     profile[(size_t)f * stride + p] = v;
 }
 
-// One thread per (pair-block, column). Subjects [first, first+count) of the shard (ascending length) form blocks
-// b = 0..ceil(count/2)-1 with members first+2b (low half) and first+2b+1 (high half, absent for an odd tail).
+// One thread per (pair-block, column). blockItem[b] names the work item (a pair of subjects) block b belongs to; the
+// block covers columns [seg*columns, (seg+1)*columns) of the pair, seg = b - item.firstBlock.
+struct PairItem { int subject0, subject1, firstBlock, numSegments; };  // same layout as sw4::S16Item
+
 __global__ void build_pair_blocks_kernel(const uint8_t* __restrict__ chars, const size_t* __restrict__ offsets,
-                                         const int32_t* __restrict__ lengths, int first, int count, int columns,
-                                         uint16_t* __restrict__ cols, int2* __restrict__ pairSubjects) {
+                                         const int32_t* __restrict__ lengths, const PairItem* __restrict__ items,
+                                         const int32_t* __restrict__ blockItem, int numBlocks, int columns,
+                                         uint16_t* __restrict__ cols) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int numBlocks = (count + 1) / 2;
     const long long total = (long long)numBlocks * columns;
     if (gid >= total) return;
     const int b = (int)(gid / columns), c = (int)(gid % columns);
-    const int s0 = first + 2 * b, s1 = s0 + 1;
-    const bool has1 = (2 * b + 1) < count;
+    const PairItem it = items[blockItem[b]];
+    const long long col = (long long)(b - it.firstBlock) * columns + c;
     int r0 = 20, r1 = 20;
-    if (c < lengths[s0]) r0 = chars[offsets[s0] + c];
-    if (has1 && c < lengths[s1]) r1 = chars[offsets[s1] + c];
+    if (it.subject0 >= 0 && col < lengths[it.subject0]) r0 = chars[offsets[it.subject0] + col];
+    if (it.subject1 >= 0 && col < lengths[it.subject1]) r1 = chars[offsets[it.subject1] + col];
     r0 = min(r0, 20); r1 = min(r1, 20);
     cols[gid] = (uint16_t)(r0 + 21 * r1);
-    if (c == 0) pairSubjects[b] = make_int2(s0, has1 ? s1 : -1);
 }
 
 }  // namespace sw4

@@ -62,16 +62,20 @@ struct Error {
 // ---------------------------------------------------------------------------------------------------------------
 // length classes of the packed 16-bit kernel: G lanes x R columns, capacity G*R
 // ---------------------------------------------------------------------------------------------------------------
-struct LengthClass { int logG, R, NA, capacity; };  // G = 1<<logG lanes x R columns, NA pair-blocks interleaved per lane
+// G = 1<<logG lanes x R columns per lane; capacity = G*R columns per pair-block. The last entry is the multi-segment
+// long class: subjects longer than 1024 are cut into segments of 1024 columns that one warp aligns back to back.
+struct LengthClass { int logG, R, capacity; bool multi; };
 static const LengthClass kLengthClasses[] = {
-    {2, 8, 1, 32},    {2, 16, 1, 64},   {2, 24, 1, 96},   {2, 32, 1, 128},  {3, 20, 1, 160},  {3, 24, 1, 192},
-    {3, 28, 1, 224},  {3, 32, 1, 256},  {4, 20, 1, 320},  {4, 24, 1, 384},  {4, 28, 1, 448},  {4, 32, 1, 512},
-    {5, 20, 1, 640},  {5, 24, 1, 768},  {5, 28, 1, 896},  {5, 32, 1, 1024},
+    {2, 8, 32, false},    {2, 16, 64, false},   {2, 24, 96, false},   {2, 32, 128, false},  {3, 20, 160, false},
+    {3, 24, 192, false},  {3, 28, 224, false},  {3, 32, 256, false},  {4, 20, 320, false},  {4, 24, 384, false},
+    {4, 28, 448, false},  {4, 32, 512, false},  {5, 20, 640, false},  {5, 24, 768, false},  {5, 28, 896, false},
+    {5, 32, 1024, false}, {5, 32, 1024, true},
 };
 constexpr int kNumLengthClasses = sizeof(kLengthClasses) / sizeof(kLengthClasses[0]);
 constexpr int kMaxS16Length = 1024;
 constexpr int kS16OverflowThreshold = 25000;  // reference MAX_ACC_SHORT, src/kernels.cuh:5
 constexpr int kHalf2Threshold = 2048;         // reference MAX_ACC_HALF2, src/kernels.cuh:4
+constexpr int kNumCounters = 8 + 32;           // [0] overflow [1] stat [2],[3] s32 tickets [4] top-k count [8+c] class tickets
 constexpr int kShardBlock = 256;              // subjects per interleaving block (even => pairs never straddle)
 
 static const int kRefBoundaries[36] = {48,  64,  80,  96,  112, 128, 144, 160, 176, 192,  208,  224,
@@ -154,11 +158,11 @@ struct DevBuf {
 };
 
 struct ClassLayout {
-    int cls = 0;            // index into kLengthClasses
+    int cls = 0;               // index into kLengthClasses
     int first = 0, count = 0;  // local subject range
-    int numBlocks = 0;
+    int numItems = 0, numBlocks = 0;
     DevBuf<uint16_t> cols;
-    DevBuf<int2> pairSubjects;
+    DevBuf<S16Item> items;
 };
 
 struct Shard {
@@ -186,9 +190,13 @@ struct Shard {
     DevBuf<uint32_t> dProfile;
     DevBuf<int8_t> dMatrix;
     DevBuf<int2> dBorder;
+    DevBuf<uint2> dBorder16;   // left/right border columns of the multi-segment class, one row array per warp
+    size_t border16Stride = 0;
     DevBuf<TopkCand> dCand;
     DevBuf<int32_t> dTopScores, dTopIds;
     // pinned host staging
+    int queryCapacity = 0, topCapacity = 0;  // what the per-scan scratch below is currently sized for
+    size_t borderWarps = 0;
     char* hQuery = nullptr; size_t hQueryCap = 0;
     int32_t* hTop = nullptr; size_t hTopCap = 0;  // scores[k], ids[k], count, ovf, stat
     int launches = 0;
@@ -205,16 +213,16 @@ struct Shard {
     }
 };
 
-template <int R, int NA>
+template <int R, bool MULTI>
 static void launch_s16(const S16Params& prm, int grid, cudaStream_t stream) {
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        SW4_CUDA(cudaFuncSetAttribute(sw_s16_kernel<R, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16_smem_bytes<R, NA>()));
+        SW4_CUDA(cudaFuncSetAttribute(sw_s16_kernel<R, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16_smem_bytes<R>()));
         configured[dev & 63] = true;
     }
-    sw_s16_kernel<R, NA><<<grid, kS16Threads, s16_smem_bytes<R, NA>(), stream>>>(prm);
+    sw_s16_kernel<R, MULTI><<<grid, kS16Threads, s16_smem_bytes<R>(), stream>>>(prm);
     SW4_CUDA(cudaGetLastError());
 }
 
@@ -336,7 +344,7 @@ struct Engine {
         sh.dGlobalIds.alloc(n);
         sh.dScores.alloc(n);
         sh.dOvfList.alloc(n);
-        sh.dCounters.alloc(8);
+        sh.dCounters.alloc(kNumCounters);
         sh.dMatrix.alloc(441);
         SW4_CUDA(cudaMemcpyAsync(sh.dChars.p, hChars, totalChars, cudaMemcpyHostToDevice, sh.stream));
         SW4_CUDA(cudaMemcpyAsync(sh.dOffsets.p, offsets.data(), (n + 1) * sizeof(size_t), cudaMemcpyHostToDevice, sh.stream));
@@ -344,35 +352,58 @@ struct Engine {
         SW4_CUDA(cudaMemcpyAsync(sh.dGlobalIds.p, sh.globalIds.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, sh.stream));
         SW4_CUDA(cudaMemsetAsync(sh.dScores.p, 0, std::max<size_t>(n, 1) * sizeof(int32_t), sh.stream));
 
-        // length classes (the shard is ascending in length)
+        // length classes (the shard is ascending in length): consecutive subjects are paired into work items
         sh.classes.clear();
         size_t pos = std::upper_bound(lengths.begin(), lengths.end(), 0) - lengths.begin();  // length-0 subjects score 0
+        std::vector<S16Item> items;
+        std::vector<int32_t> blockItem;
         for (int c = 0; c < kNumLengthClasses; c++) {
-            const size_t end = std::upper_bound(lengths.begin(), lengths.end(), kLengthClasses[c].capacity) - lengths.begin();
+            const LengthClass& lc = kLengthClasses[c];
+            const size_t end = lc.multi ? n : std::upper_bound(lengths.begin(), lengths.end(), lc.capacity) - lengths.begin();
             if (end > pos) {
                 auto cl = std::make_unique<ClassLayout>();
                 cl->cls = c;
                 cl->first = (int)pos;
                 cl->count = (int)(end - pos);
-                cl->numBlocks = (cl->count + 1) / 2;
-                const int columns = kLengthClasses[c].capacity;
+                items.clear();
+                blockItem.clear();
+                for (size_t i = pos; i < end; i += 2) {
+                    S16Item it;
+                    it.subject0 = (int)i;
+                    it.subject1 = (i + 1 < end) ? (int)(i + 1) : -1;
+                    const int maxLen = std::max(lengths[i], (i + 1 < end) ? lengths[i + 1] : 0);
+                    it.numSegments = lc.multi ? (maxLen + lc.capacity - 1) / lc.capacity : 1;
+                    it.firstBlock = 0;
+                    items.push_back(it);
+                }
+                if (lc.multi) std::reverse(items.begin(), items.end());  // longest first: they bound the makespan
+                int blk = 0;
+                for (size_t k = 0; k < items.size(); k++) {
+                    items[k].firstBlock = blk;
+                    for (int sgm = 0; sgm < items[k].numSegments; sgm++) blockItem.push_back((int32_t)k);
+                    blk += items[k].numSegments;
+                }
+                cl->numItems = (int)items.size();
+                cl->numBlocks = blk;
+                const int columns = lc.capacity;
                 cl->cols.alloc((size_t)cl->numBlocks * columns);
-                cl->pairSubjects.alloc(cl->numBlocks);
+                cl->items.alloc(items.size());
+                DevBuf<int32_t> dBlockItem;
+                dBlockItem.alloc(blockItem.size());
+                SW4_CUDA(cudaMemcpyAsync(cl->items.p, items.data(), items.size() * sizeof(S16Item), cudaMemcpyHostToDevice, sh.stream));
+                SW4_CUDA(cudaMemcpyAsync(dBlockItem.p, blockItem.data(), blockItem.size() * sizeof(int32_t), cudaMemcpyHostToDevice, sh.stream));
                 const long long total = (long long)cl->numBlocks * columns;
                 build_pair_blocks_kernel<<<(unsigned)((total + 255) / 256), 256, 0, sh.stream>>>(
-                    sh.dChars.p, sh.dOffsets.p, sh.dLengths.p, cl->first, cl->count, columns, cl->cols.p, cl->pairSubjects.p);
+                    sh.dChars.p, sh.dOffsets.p, sh.dLengths.p, reinterpret_cast<const PairItem*>(cl->items.p), dBlockItem.p,
+                    cl->numBlocks, columns, cl->cols.p);
                 SW4_CUDA(cudaGetLastError());
+                SW4_CUDA(cudaStreamSynchronize(sh.stream));  // dBlockItem and the host vectors go out of scope
                 sh.classes.push_back(std::move(cl));
             }
             pos = std::max(pos, end);
         }
-        sh.numLong = (int)(n - pos);
-        sh.dLongList.alloc(std::max(1, sh.numLong));
-        if (sh.numLong) {
-            std::vector<int32_t> ll(sh.numLong);
-            for (int i = 0; i < sh.numLong; i++) ll[i] = (int32_t)(pos + i);
-            SW4_CUDA(cudaMemcpyAsync(sh.dLongList.p, ll.data(), ll.size() * sizeof(int32_t), cudaMemcpyHostToDevice, sh.stream));
-        }
+        sh.numLong = 0;
+        sh.dLongList.alloc(1);
         SW4_CUDA(cudaStreamSynchronize(sh.stream));
         sh.uploaded = true;
         if (verbose)
@@ -382,8 +413,14 @@ struct Engine {
 
     void upload() {
         if (!db) fail(SW4_ERR_INVALID, "no database set");
+        bool fresh = false;
         for (auto& sh : shards)
-            if (!sh->uploaded) uploadShard(*sh);
+            if (!sh->uploaded) { uploadShard(*sh); fresh = true; }
+        if (fresh) {  // untimed warm-up scan: loads every kernel this shard will launch and sizes the scratch buffers
+            const int k = (int)std::min<size_t>((size_t)std::max(numTop, 1), std::max<size_t>(db->n, 1));
+            for (auto& sh : shards) enqueueScan(*sh, "ARNDCQEGHILKMFPSTWYV", 20, std::min(k, kTopkMaxCandidates / 2));
+            for (auto& sh : shards) { SW4_CUDA(cudaSetDevice(sh->device)); SW4_CUDA(cudaStreamSynchronize(sh->stream)); }
+        }
     }
 
     // ---- one scan on one shard: everything is enqueued on sh.stream ----
@@ -396,7 +433,7 @@ struct Engine {
         if ((size_t)qlen > sh.hQueryCap) {
             if (sh.hQuery) cudaFreeHost(sh.hQuery);
             sh.hQuery = nullptr;
-            sh.hQueryCap = (size_t)qlen + 4096;
+            sh.hQueryCap = std::max<size_t>((size_t)qlen * 2, 65536);
             SW4_CUDA(cudaMallocHost(&sh.hQuery, sh.hQueryCap));
         }
         const size_t topWords = (size_t)2 * k + 8;
@@ -407,18 +444,38 @@ struct Engine {
             SW4_CUDA(cudaMallocHost(&sh.hTop, sh.hTopCap * sizeof(int32_t)));
         }
         const int profStride = (qlen + 31 + 3) / 4 * 4 + 16;
-        sh.dQueryLetters.ensure((size_t)qlen + 16);
-        sh.dQueryCodes.ensure((size_t)qpad + 16);
-        sh.dProfile.ensure((size_t)kFused * profStride);
-        sh.dTopScores.ensure(k);
-        sh.dTopIds.ensure(k);
+        // All device scratch is sized here, BEFORE the timed region, for a query capacity that only grows by doubling:
+        // cudaMalloc/cudaFree inside the event-bracketed region stall the stream for up to hundreds of milliseconds.
+        if (qlen > sh.queryCapacity || k > sh.topCapacity) {
+            SW4_CUDA(cudaStreamSynchronize(sh.stream));
+            int cap = std::max(sh.queryCapacity, 8192);
+            while (cap < qlen) cap *= 2;
+            sh.queryCapacity = cap;
+            sh.topCapacity = std::max(sh.topCapacity, std::max(k, 64));
+            const size_t capStride = (size_t)(cap + 31 + 3) / 4 * 4 + 16;
+            sh.dQueryLetters.ensure((size_t)cap + 16);
+            sh.dQueryCodes.ensure((size_t)cap + 16);
+            sh.dProfile.ensure((size_t)kFused * capStride);
+            sh.dTopScores.ensure(sh.topCapacity);
+            sh.dTopIds.ensure(sh.topCapacity);
+            sh.dCand.ensure((size_t)kTopkMaxCandidates);
+            const size_t capBorderStride = (size_t)(cap + 31) / 32 * 32 + 32;
+            sh.borderWarps = (size_t)sh.smCount * 4 * kS32WarpsPerBlock;
+            while (sh.borderWarps * capBorderStride * sizeof(int2) > mem.max_temp_bytes && sh.borderWarps > kS32WarpsPerBlock)
+                sh.borderWarps = (sh.borderWarps / 2 + kS32WarpsPerBlock - 1) / kS32WarpsPerBlock * kS32WarpsPerBlock;
+            sh.dBorder.ensure(sh.borderWarps * capBorderStride);
+            bool anyMulti = false;
+            for (auto& cl : sh.classes) anyMulti |= kLengthClasses[cl->cls].multi;
+            sh.border16Stride = capBorderStride;
+            sh.dBorder16.ensure(anyMulti ? (size_t)sh.smCount * kS16Warps * capBorderStride : 1);
+        }
         memcpy(sh.hQuery, query, (size_t)qlen);
 
         cudaStream_t st = sh.stream;
         SW4_CUDA(cudaEventRecord(sh.evStart, st));
         SW4_CUDA(cudaMemcpyAsync(sh.dQueryLetters.p, sh.hQuery, (size_t)qlen, cudaMemcpyHostToDevice, st));
         SW4_CUDA(cudaMemcpyAsync(sh.dMatrix.p, matrix, 441, cudaMemcpyHostToDevice, st));
-        SW4_CUDA(cudaMemsetAsync(sh.dCounters.p, 0, 8 * sizeof(int), st));
+        SW4_CUDA(cudaMemsetAsync(sh.dCounters.p, 0, kNumCounters * sizeof(int), st));
         if (qlen == 0) SW4_CUDA(cudaMemsetAsync(sh.dScores.p, 0, std::max<size_t>(sh.n, 1) * sizeof(int32_t), st));
         if (qpad > 0) convert_query_kernel<<<(qpad + 255) / 256, 256, 0, st>>>(sh.dQueryLetters.p, sh.dQueryCodes.p, qlen, qpad);
         build_profile_kernel<<<dim3((profStride + 127) / 128, kFused), 128, 0, st>>>(sh.dQueryCodes.p, qlen, sh.dMatrix.p,
@@ -436,8 +493,9 @@ struct Engine {
             const int G = 1 << lc.logG;
             S16Params prm{};
             prm.cols = cl.cols.p;
-            prm.pairSubjects = cl.pairSubjects.p;
-            prm.numBlocks = cl.numBlocks;
+            prm.items = cl.items.p;
+            prm.numItems = cl.numItems;
+            prm.ticket = sh.dCounters.p + 8 + cl.cls;
             prm.logG = lc.logG;
             prm.profile = sh.dProfile.p;
             prm.profStride = profStride;
@@ -451,18 +509,22 @@ struct Engine {
             prm.ovfList = sh.dOvfList.p;
             prm.ovfCount = sh.dCounters.p + 0;
             prm.statCount = sh.dCounters.p + 1;
+            prm.border = sh.dBorder16.p;
+            prm.borderStride = (int)sh.border16Stride;
             const int groupsPerCta = kS16Warps * (32 >> lc.logG);
-            const int superBlocks = (cl.numBlocks + lc.NA - 1) / lc.NA;
-            const int grid = std::max(1, std::min(sh.smCount, (superBlocks + groupsPerCta - 1) / groupsPerCta));
-            const int key = lc.R * 10 + lc.NA;
-            switch (key) {
-                case 81: launch_s16<8, 1>(prm, grid, st); break;
-                case 161: launch_s16<16, 1>(prm, grid, st); break;
-                case 201: launch_s16<20, 1>(prm, grid, st); break;
-                case 241: launch_s16<24, 1>(prm, grid, st); break;
-                case 281: launch_s16<28, 1>(prm, grid, st); break;
-                case 321: launch_s16<32, 1>(prm, grid, st); break;
-                default: fail(SW4_ERR_INVALID, "no kernel for R=%d NA=%d", lc.R, lc.NA);
+            const int grid = std::max(1, std::min(sh.smCount, (cl.numItems + groupsPerCta - 1) / groupsPerCta));
+            if (lc.multi) {
+                launch_s16<32, true>(prm, grid, st);
+            } else {
+                switch (lc.R) {
+                    case 8: launch_s16<8, false>(prm, grid, st); break;
+                    case 16: launch_s16<16, false>(prm, grid, st); break;
+                    case 20: launch_s16<20, false>(prm, grid, st); break;
+                    case 24: launch_s16<24, false>(prm, grid, st); break;
+                    case 28: launch_s16<28, false>(prm, grid, st); break;
+                    case 32: launch_s16<32, false>(prm, grid, st); break;
+                    default: fail(SW4_ERR_INVALID, "no kernel for R=%d", lc.R);
+                }
             }
             sh.launches++;
         }
@@ -470,14 +532,8 @@ struct Engine {
         // exact 32-bit path: long subjects, then whatever saturated in 16 bit
         const int borderStride = (qlen + 31) / 32 * 32 + 32;
         auto launchS32 = [&](const int32_t* list, const int* countPtr, int countHost, int* ticket, bool countStats) {
-            int blocks = sh.smCount * 4;
+            int blocks = (int)(sh.borderWarps / kS32WarpsPerBlock);
             if (!countPtr) blocks = std::max(1, std::min(blocks, (countHost + kS32WarpsPerBlock - 1) / kS32WarpsPerBlock));
-            size_t warps = (size_t)blocks * kS32WarpsPerBlock;
-            while (warps * borderStride * sizeof(int2) > mem.max_temp_bytes && blocks > 1) {
-                blocks = (blocks + 1) / 2;
-                warps = (size_t)blocks * kS32WarpsPerBlock;
-            }
-            sh.dBorder.ensure(warps * borderStride);
             S32Params p{};
             p.chars = sh.dChars.p; p.offsets = sh.dOffsets.p; p.lengths = sh.dLengths.p;
             p.list = list; p.listCountPtr = countPtr; p.listCountHost = countHost;
@@ -500,7 +556,6 @@ struct Engine {
         if (k > 0 && n > 0) {
             int blocks = (int)std::min<long long>(std::min<long long>(2LL * sh.smCount, kTopkMaxCandidates / k), (n + 4095) / 4096);
             blocks = std::max(blocks, 1);
-            sh.dCand.ensure((size_t)blocks * k);
             topk_pass1_kernel<<<blocks, kTopkThreads, 0, st>>>(sh.dScores.p, nullptr, n, k, sh.dCand.p);
             const int numCand = blocks * k;
             int n2 = 1;

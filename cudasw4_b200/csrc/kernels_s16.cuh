@@ -37,10 +37,20 @@ constexpr int kFillBatch = 16;             // steps between ring refills / CTA b
 constexpr int kRingBytes = kFused * kRingStride * 4;
 constexpr short kNegS16 = -16000;
 
+// One unit of work for a group: a pair of subjects occupying `numSegments` consecutive pair-blocks (1 for every
+// subject that fits the class's G*R columns; > 1 only in the multi-segment long class, where segment s holds columns
+// [s*G*R, (s+1)*G*R) and the last column's (H, E) of every query row is handed to the next segment through `border`).
+struct S16Item {
+    int subject0, subject1;   // local subject index of the low / high half (-1 = none)
+    int firstBlock;           // index of the first pair-block in `cols`
+    int numSegments;
+};
+
 struct S16Params {
     const uint16_t* cols;        // [numBlocks][G*R] fused column codes, lane-major (lane m owns [m*R, m*R+R))
-    const int2* pairSubjects;    // [numBlocks] local subject index of the low / high half (-1 = none)
-    int numBlocks;
+    const S16Item* items;        // [numItems] in the order they should be started
+    int numItems;
+    int* ticket;                 // zero-initialised work counter (items are handed out dynamically)
     int logG;                    // G = 1 << logG lanes per group
     const uint32_t* profile;     // [441][profStride] positional query profile
     int profStride;
@@ -53,13 +63,10 @@ struct S16Params {
     int32_t* ovfList;            // local subject indices that need the exact 32-bit path
     int* ovfCount;
     int* statCount;
+    uint2* border;               // MULTI only: [gridWarps][borderStride] (H, E) of a segment's last column per query row
+    int borderStride;
 };
 
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
 template <int N, class Fn, int... Is>
 __device__ __forceinline__ void static_for_impl(Fn&& fn, std::integer_sequence<int, Is...>) {
     (fn(std::integral_constant<int, Is>{}), ...);
@@ -85,8 +92,10 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int R, int NA>
-constexpr int s16_smem_bytes() { return kRingBytes + kS16Warps * 32 * NA * R * 2; }
+constexpr int kGroupStateInts = 8;  // per-group bookkeeping kept in shared memory (touched at restarts only)
+
+template <int R>
+constexpr int s16_smem_bytes() { return kRingBytes + kS16Warps * 32 * R * 2 + kS16Warps * 8 * kGroupStateInts * 4; }
 
 // Refill ring slots for global steps [x0, x0+16) (x0 % 16 == 0); p0 = x0 mod period.
 __device__ __forceinline__ void ring_fill(uint32_t ringBase, const uint32_t* __restrict__ profile, int profStride, int x0,
@@ -106,60 +115,66 @@ __device__ __forceinline__ void ring_fill(uint32_t ringBase, const uint32_t* __r
     cp_async_commit();
 }
 
-// R  = register columns per alignment per lane, NA = alignments (pair-blocks) interleaved per lane. NA = 2 gives every
-// warp two independent E/H dependency chains, which is what lets 4 warps per scheduler keep the ALU pipe busy.
-template <int R, int NA>
+// R = register columns per lane. MULTI = the long class: G must be 32 and an item may span several segments.
+template <int R, bool MULTI>
 __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params prm) {
     static_assert(R % 4 == 0, "a lane's staging slice (R u16 codes) must be a whole number of 8-byte chunks");
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t ringBase = (uint32_t)__cvta_generic_to_shared(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int logG = prm.logG, G = 1 << logG;
+    const int logG = MULTI ? 5 : prm.logG, G = 1 << logG;
     const int g = lane >> logG, m = lane & (G - 1);
-    const int groupsPerWarp = 32 >> logG;
-    const int totalGroups = gridDim.x * kS16Warps * groupsPerWarp;
     const int P = prm.period;
-    const int superBlocks = (prm.numBlocks + NA - 1) / NA;  // a group aligns NA consecutive pair-blocks at a time
-    const int rounds = (superBlocks + totalGroups - 1) / totalGroups;
     const unsigned groupMask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (g << logG));
+    const int leader = g << logG;  // lane index of the group's first lane
 
-    // this lane's slice of the group's staging area: NA x R fused u16 column codes of the next pair-blocks
-    const uint32_t stageLane = ringBase + kRingBytes + (warp * 32 + lane) * (NA * R * 2);
+    // this lane's slice of the group's staging area: R fused u16 column codes of the next pair-block
+    const uint32_t stageLane = ringBase + kRingBytes + (warp * 32 + lane) * (R * 2);
+    // group state in shared memory: [0] subject0 [1] subject1 [2] segments left after the current one
+    // [3] look-ahead valid [4] look-ahead block [5] look-ahead starts a new item [6] look-ahead item index
+    volatile int* gs = reinterpret_cast<volatile int*>(smem + kRingBytes + kS16Warps * 32 * R * 2) +
+                       (warp * 8 + g) * kGroupStateInts;
+    uint2* border = MULTI ? prm.border + (size_t)(blockIdx.x * kS16Warps + warp) * prm.borderStride : nullptr;
 
-    uint32_t colAddr[NA][R];  // ring byte address of this column's fused-pair row (lane and batch-phase offsets folded in)
-    uint32_t Hp[NA][R];       // H of the previous row
-    uint32_t F[NA][R];        // F for the next row
+    uint32_t colAddr[R];  // ring byte address of this column's fused-pair row (lane and batch-phase offsets folded in)
+    uint32_t Hp[R];       // H of the previous row
+    uint32_t F[R];        // F for the next row
     const uint32_t NEG2 = ((uint32_t)(uint16_t)kNegS16 << 16) | (uint16_t)kNegS16;
-    uint32_t mx[NA], Elast[NA], HinPrev[NA];
+    uint32_t mx = 0, Elast = NEG2, HinPrev = 0;
 #pragma unroll
-    for (int a = 0; a < NA; a++) {
-        mx[a] = 0; Elast[a] = NEG2; HinPrev[a] = 0;
-#pragma unroll
-        for (int j = 0; j < R; j++) { colAddr[a][j] = ringBase; Hp[a][j] = 0; F[a][j] = NEG2; }
-    }
-    // p = this lane's row in the period-P schedule, (t - lane) mod P. The group restarts (stores the finished pairs,
-    // loads the next ones) when its first lane is at row 0, i.e. when this lane is at row pRestart.
+    for (int j = 0; j < R; j++) { colAddr[j] = ringBase; Hp[j] = 0; F[j] = NEG2; }
+    // p = this lane's row in the period-P schedule, (t - lane) mod P. The group restarts (stores the finished pair,
+    // loads the next one) when its first lane is at row 0, i.e. when this lane is at row pRestart.
     int p = (lane == 0) ? 0 : P - lane;
     const int pRestart = (m == 0) ? 0 : P - m;
-    int nextSuper = (blockIdx.x * kS16Warps + warp) * groupsPerWarp + g;  // super-block index of the NEXT alignments
-    bool haveWork = false;
+    bool haveWork = false;    // a segment is being computed
+    bool useBorder = false;   // MULTI: the current segment continues an item (left border comes from `border`)
+    bool alive = true;        // the group still has something to compute, finalise or start
+    uint2 inBuf = make_uint2(0, NEG2), outBuf = make_uint2(0, 0);
 
-    auto prefetch_blocks = [&](int super) {  // lane m copies its R columns of each of the NA blocks
+    // look-ahead: fetch the descriptor of the item / segment that follows and start copying its columns
+    auto fetch_lookahead = [&](bool continuing, int curBlock) {
+        int blk = -1, isNew = 0, item = -1;
+        if (continuing) {
+            blk = curBlock + 1;
+        } else {
+            if (m == 0) item = atomicAdd(prm.ticket, 1);
+            item = __shfl_sync(groupMask, item, leader);
+            if (item < prm.numItems) { blk = prm.items[item].firstBlock; isNew = 1; }
+        }
+        if (m == 0) { gs[3] = blk >= 0; gs[4] = blk; gs[5] = isNew; gs[6] = item; }
+        if (blk >= 0) {
+            const unsigned char* src = (const unsigned char*)(prm.cols + (size_t)blk * (G * R)) + m * (R * 2);
+            if constexpr ((R * 2) % 16 == 0) {
 #pragma unroll
-        for (int a = 0; a < NA; a++) {
-            const int blk = super * NA + a;
-            if (super < superBlocks && blk < prm.numBlocks) {
-                const unsigned char* src = (const unsigned char*)(prm.cols + (size_t)blk * (G * R)) + m * (R * 2);
-                if constexpr ((R * 2) % 16 == 0) {
+                for (int i = 0; i < R * 2 / 16; i++) cp_async16(stageLane + i * 16, src + i * 16);
+            } else {
 #pragma unroll
-                    for (int i = 0; i < R * 2 / 16; i++) cp_async16(stageLane + a * R * 2 + i * 16, src + i * 16);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < R * 2 / 8; i++) cp_async8(stageLane + a * R * 2 + i * 8, src + i * 8);
-                }
+                for (int i = 0; i < R * 2 / 8; i++) cp_async8(stageLane + i * 8, src + i * 8);
             }
         }
         cp_async_commit();
+        __syncwarp(groupMask);
     };
 
     // prologue: lanes l > 0 run their first l steps at "negative time" (rows before the query starts): those ring
@@ -167,18 +182,17 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
     for (int i = threadIdx.x; i < kFused * kRingStride; i += kS16Threads) reinterpret_cast<uint32_t*>(smem)[i] = NEG2;
     __syncthreads();
     ring_fill(ringBase, prm.profile, prm.profStride, 0, 0, P);
-    prefetch_blocks(nextSuper);
+    fetch_lookahead(false, 0);
     int pfill = kFillBatch % P;  // (next fill start) mod P
 
     // The step offset inside the ring is an instruction immediate: 16 steps are unrolled and the column addresses are
     // advanced by 64 bytes once per batch (ptxas does not fold a uniform register into LDS addresses, and an
     // address add per cell would cost an issue slot per cell-pair).
     uint32_t phaseBase = ringBase + (32 - lane) * 4;  // + 64 bytes per batch, wrapping every 4 batches
-    const int numBatches = (rounds * P + 32 + kFillBatch - 1) / kFillBatch;
 #pragma unroll 1
-    for (int batch = 0; batch < numBatches; ++batch) {
+    for (int batch = 0;; ++batch) {
         cp_async_wait_all();
-        __syncthreads();
+        if (!__syncthreads_or(alive)) break;
         ring_fill(ringBase, prm.profile, prm.profStride, (batch + 1) * kFillBatch, pfill, P);
         pfill += kFillBatch;
         while (pfill >= P) pfill -= P;
@@ -186,94 +200,119 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
             const int delta = (batch & 3) ? kFillBatch * 4 : -(kRingSlots - kFillBatch) * 4;
             phaseBase += delta;
 #pragma unroll
-            for (int a = 0; a < NA; a++)
-#pragma unroll
-                for (int j = 0; j < R; j++) colAddr[a][j] += delta;
+            for (int j = 0; j < R; j++) colAddr[j] += delta;
         }
         static_for<kFillBatch>([&](auto stepIndex) {
             constexpr int i = decltype(stepIndex)::value;
-            if ((i & 3) == 0 && p == pRestart) {  // group restart: uniform within the group, divergent across groups
-                if (haveWork) {
-#pragma unroll
-                    for (int a = 0; a < NA; a++) {
-                        uint32_t r = mx[a];
-                        for (int o = G >> 1; o > 0; o >>= 1) r = __vmaxs2(r, __shfl_xor_sync(groupMask, r, o));
-                        const int blk = (nextSuper - totalGroups) * NA + a;
-                        if (m == 0 && blk < prm.numBlocks) {
-                            const int2 subj = prm.pairSubjects[blk];
-                            const int lo = (int)(short)(r & 0xffff), hi = (int)(short)(r >> 16);
-                            if (subj.x >= 0) {
-                                if (lo >= prm.statThreshold) atomicAdd(prm.statCount, 1);
-                                if (lo >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = subj.x;
-                                prm.scores[subj.x] = lo;
-                            }
-                            if (subj.y >= 0) {
-                                if (hi >= prm.statThreshold) atomicAdd(prm.statCount, 1);
-                                if (hi >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = subj.y;
-                                prm.scores[subj.y] = hi;
-                            }
+            if ((i & 3) == 0 && p == pRestart && alive) {  // group restart: uniform in the group, divergent across groups
+                __syncwarp(groupMask);
+                int segsLeft = gs[2];
+                if (haveWork && segsLeft == 0) {  // the item is complete: reduce the maxima and store the two scores
+                    uint32_t r = mx;
+                    for (int o = G >> 1; o > 0; o >>= 1) r = __vmaxs2(r, __shfl_xor_sync(groupMask, r, o));
+                    if (m == 0) {
+                        const int s0 = gs[0], s1 = gs[1];
+                        const int lo = (int)(short)(r & 0xffff), hi = (int)(short)(r >> 16);
+                        if (s0 >= 0) {
+                            if (lo >= prm.statThreshold) atomicAdd(prm.statCount, 1);
+                            if (lo >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = s0;
+                            prm.scores[s0] = lo;
+                        }
+                        if (s1 >= 0) {
+                            if (hi >= prm.statThreshold) atomicAdd(prm.statCount, 1);
+                            if (hi >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = s1;
+                            prm.scores[s1] = hi;
                         }
                     }
                 }
-                haveWork = nextSuper < superBlocks;
-                if (haveWork) {
+                const bool laValid = gs[3] != 0;
+                const int laBlk = gs[4];
+                const bool laNew = gs[5] != 0;
+                haveWork = laValid;
+                alive = laValid;
+                if (laValid) {
+                    if (laNew) {
+                        const S16Item it = prm.items[gs[6]];
+                        __syncwarp(groupMask);
+                        if (m == 0) { gs[0] = it.subject0; gs[1] = it.subject1; gs[2] = it.numSegments - 1; }
+                        segsLeft = it.numSegments - 1;
+                        mx = 0;
+                        useBorder = false;
+                    } else {
+                        __syncwarp(groupMask);
+                        if (m == 0) gs[2] = segsLeft - 1;
+                        segsLeft -= 1;
+                        useBorder = true;
+                    }
                     cp_async_wait_all();
                     __syncwarp(groupMask);
 #pragma unroll
-                    for (int a = 0; a < NA; a++) {
-#pragma unroll
-                        for (int b = 0; b < R / 2; b++) {
-                            const uint32_t w = lds_u32_imm<0>(stageLane + (a * R + b * 2) * 2);
-                            colAddr[a][b * 2 + 0] = phaseBase + (w & 0xffffu) * (kRingStride * 4);
-                            colAddr[a][b * 2 + 1] = phaseBase + (w >> 16) * (kRingStride * 4);
-                        }
-#pragma unroll
-                        for (int j = 0; j < R; j++) { Hp[a][j] = 0; F[a][j] = NEG2; }
-                        mx[a] = 0; HinPrev[a] = 0;
+                    for (int b = 0; b < R / 2; b++) {
+                        const uint32_t w = lds_u32_imm<0>(stageLane + b * 4);
+                        colAddr[b * 2 + 0] = phaseBase + (w & 0xffffu) * (kRingStride * 4);
+                        colAddr[b * 2 + 1] = phaseBase + (w >> 16) * (kRingStride * 4);
                     }
+#pragma unroll
+                    for (int j = 0; j < R; j++) { Hp[j] = 0; F[j] = NEG2; }
+                    HinPrev = 0;
                     __syncwarp(groupMask);
-                    prefetch_blocks(nextSuper + totalGroups);
+                    fetch_lookahead(segsLeft > 0, laBlk);
                 }
-                nextSuper += totalGroups;
             }
+            // systolic hand-over from the previous lane (row p was computed there one step earlier)
+            uint32_t Hin = __shfl_up_sync(0xffffffffu, Hp[R - 1], 1);
+            uint32_t Ein = __shfl_up_sync(0xffffffffu, Elast, 1);
             // Rows p >= q are "gap rows" between two alignments of the group: they are computed like any other row (no
             // branch => no register shuffling at a merge point) on profile entries of -16000, with the hand-over
             // inputs forced to the boundary values so that nothing leaks into the freshly reset state; they can
             // never raise the running maximum.
-            const bool boundary = (m == 0) || ((unsigned)p >= (unsigned)prm.qlen);
-            uint32_t E[NA], d[NA], dPrev[NA];
-#pragma unroll
-            for (int a = 0; a < NA; a++) {
-                // systolic hand-over from the previous lane (row p was computed there one step earlier)
-                uint32_t Hin = __shfl_up_sync(0xffffffffu, Hp[a][R - 1], 1);
-                uint32_t Ein = __shfl_up_sync(0xffffffffu, Elast[a], 1);
-                if (boundary) { Hin = 0; Ein = NEG2; }
-                E[a] = Ein;
-                d[a] = __vadd2(HinPrev[a], lds_u32_imm<i * 4>(colAddr[a][0]));
-                dPrev[a] = 0;
-                HinPrev[a] = Hin;
+            const bool realRow = (unsigned)p < (unsigned)prm.qlen;
+            if constexpr (MULTI) {
+                // left border of a continued item: 32 rows at a time, coalesced; lane 0 is at row p
+                const int p0 = __shfl_sync(0xffffffffu, p, 0);
+                if ((p0 & 31) == 0 && p0 < prm.qlen) inBuf = useBorder ? border[p0 + lane] : make_uint2(0, NEG2);
+                const uint32_t bH = __shfl_sync(0xffffffffu, inBuf.x, p0 & 31);
+                const uint32_t bE = __shfl_sync(0xffffffffu, inBuf.y, p0 & 31);
+                if (m == 0) { Hin = bH; Ein = bE; }
+                if (!realRow) { Hin = 0; Ein = NEG2; }
+            } else {
+                if (m == 0 || !realRow) { Hin = 0; Ein = NEG2; }
             }
+            {
+                uint32_t E = Ein;
+                uint32_t d = __vadd2(HinPrev, lds_u32_imm<i * 4>(colAddr[0]));
+                uint32_t dPrev = 0;
 #pragma unroll
-            for (int j = 0; j < R; j++) {
-#pragma unroll
-                for (int a = 0; a < NA; a++) {
+                for (int j = 0; j < R; j++) {
                     // look-ahead: the next column's diagonal term reads Hp[j] before this column overwrites it
                     uint32_t dNext = 0;
-                    if (j + 1 < R) dNext = __vadd2(Hp[a][j], lds_u32_imm<i * 4>(colAddr[a][j + 1]));
-                    const uint32_t h = __vimax3_s16x2_relu(d[a], E[a], F[a][j]);
-                    Hp[a][j] = h;
+                    if (j + 1 < R) dNext = __vadd2(Hp[j], lds_u32_imm<i * 4>(colAddr[j + 1]));
+                    const uint32_t h = __vimax3_s16x2_relu(d, E, F[j]);
+                    Hp[j] = h;
                     const uint32_t tt = __vadd2(h, prm.gop2);
-                    E[a] = __viaddmax_s16x2(E[a], prm.gex2, tt);
-                    F[a][j] = __viaddmax_s16x2(F[a][j], prm.gex2, tt);
+                    E = __viaddmax_s16x2(E, prm.gex2, tt);
+                    F[j] = __viaddmax_s16x2(F[j], prm.gex2, tt);
                     // max over d == max over H: a best local alignment ends on a match, and d having a second use
                     // keeps ptxas from fusing the add into an ALU-pipe VIADDMNMX
-                    if (j & 1) mx[a] = __vimax3_s16x2(mx[a], d[a], dPrev[a]);
-                    dPrev[a] = d[a];
-                    d[a] = dNext;
+                    if (j & 1) mx = __vimax3_s16x2(mx, d, dPrev);
+                    dPrev = d;
+                    d = dNext;
+                }
+                Elast = E;
+                HinPrev = Hin;
+            }
+            if constexpr (MULTI) {
+                // right border: lane 31 has just finished its row p31; collect 32 rows, then store them coalesced
+                const int p31 = __shfl_sync(0xffffffffu, p, 31);
+                const uint32_t vH = __shfl_sync(0xffffffffu, Hp[R - 1], 31);
+                const uint32_t vE = __shfl_sync(0xffffffffu, Elast, 31);
+                if (p31 < prm.qlen && haveWork) {
+                    if (lane == (p31 & 31)) outBuf = make_uint2(vH, vE);
+                    if ((p31 & 31) == 31 || p31 == prm.qlen - 1) {
+                        if (lane <= (p31 & 31)) border[(p31 & ~31) + lane] = outBuf;
+                    }
                 }
             }
-#pragma unroll
-            for (int a = 0; a < NA; a++) Elast[a] = E[a];
             if (++p == P) p = 0;
         });
     }
