@@ -161,15 +161,22 @@ struct ClassLayout {
     int cls = 0;               // index into kLengthClasses
     int first = 0, count = 0;  // local subject range
     int numItems = 0, numBlocks = 0;
+    double rate = 1.0;         // measured SM-milliseconds per unit of modelled cost (feedback for the SM partition)
+    double lastCost = 0;
+    int lastGrid = 0;
     DevBuf<uint16_t> cols;
     DevBuf<S16Item> items;
 };
+
+constexpr int kMaxClassStreams = 24;
 
 struct Shard {
     int device = 0;
     int smCount = 148;
     cudaStream_t stream = nullptr;
-    cudaEvent_t evStart = nullptr, evK0 = nullptr, evK1 = nullptr, evStop = nullptr;
+    cudaEvent_t evStart = nullptr, evK0 = nullptr, evK1 = nullptr, evStop = nullptr, evFork = nullptr;
+    cudaStream_t classStreams[kMaxClassStreams] = {};
+    cudaEvent_t evJoin[kMaxClassStreams] = {};
     // subject selection
     std::vector<int32_t> globalIds;  // local index -> global id (ascending)
     uint64_t residues = 0;
@@ -190,6 +197,8 @@ struct Shard {
     DevBuf<uint32_t> dProfile;
     DevBuf<int8_t> dMatrix;
     DevBuf<int2> dBorder;
+    DevBuf<unsigned long long> dClassNs;  // per length class: run time of its last launch (written by the kernel)
+    unsigned long long* hClassNs = nullptr;
     DevBuf<uint2> dBorder16;   // left/right border columns of the multi-segment class, one row array per warp
     size_t border16Stride = 0;
     DevBuf<TopkCand> dCand;
@@ -205,10 +214,16 @@ struct Shard {
         cudaSetDevice(device);
         if (hQuery) cudaFreeHost(hQuery);
         if (hTop) cudaFreeHost(hTop);
+        if (hClassNs) cudaFreeHost(hClassNs);
         if (evStart) cudaEventDestroy(evStart);
         if (evK0) cudaEventDestroy(evK0);
         if (evK1) cudaEventDestroy(evK1);
         if (evStop) cudaEventDestroy(evStop);
+        if (evFork) cudaEventDestroy(evFork);
+        for (int i = 0; i < kMaxClassStreams; i++) {
+            if (evJoin[i]) cudaEventDestroy(evJoin[i]);
+            if (classStreams[i]) cudaStreamDestroy(classStreams[i]);
+        }
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -297,6 +312,11 @@ struct Engine {
             SW4_CUDA(cudaEventCreate(&sh.evK0));
             SW4_CUDA(cudaEventCreate(&sh.evK1));
             SW4_CUDA(cudaEventCreate(&sh.evStop));
+            SW4_CUDA(cudaEventCreateWithFlags(&sh.evFork, cudaEventDisableTiming));
+            for (int i = 0; i < kMaxClassStreams; i++) {
+                SW4_CUDA(cudaStreamCreateWithFlags(&sh.classStreams[i], cudaStreamNonBlocking));
+                SW4_CUDA(cudaEventCreateWithFlags(&sh.evJoin[i], cudaEventDisableTiming));
+            }
         }
     }
 
@@ -345,6 +365,8 @@ struct Engine {
         sh.dScores.alloc(n);
         sh.dOvfList.alloc(n);
         sh.dCounters.alloc(kNumCounters);
+        sh.dClassNs.alloc(32);
+        if (!sh.hClassNs) SW4_CUDA(cudaMallocHost(&sh.hClassNs, 32 * sizeof(unsigned long long)));
         sh.dMatrix.alloc(441);
         SW4_CUDA(cudaMemcpyAsync(sh.dChars.p, hChars, totalChars, cudaMemcpyHostToDevice, sh.stream));
         SW4_CUDA(cudaMemcpyAsync(sh.dOffsets.p, offsets.data(), (n + 1) * sizeof(size_t), cudaMemcpyHostToDevice, sh.stream));
@@ -418,8 +440,13 @@ struct Engine {
             if (!sh->uploaded) { uploadShard(*sh); fresh = true; }
         if (fresh) {  // untimed warm-up scan: loads every kernel this shard will launch and sizes the scratch buffers
             const int k = (int)std::min<size_t>((size_t)std::max(numTop, 1), std::max<size_t>(db->n, 1));
-            for (auto& sh : shards) enqueueScan(*sh, "ARNDCQEGHILKMFPSTWYV", 20, std::min(k, kTopkMaxCandidates / 2));
-            for (auto& sh : shards) { SW4_CUDA(cudaSetDevice(sh->device)); SW4_CUDA(cudaStreamSynchronize(sh->stream)); }
+            std::string warm;
+            for (int i = 0; i < 320; i++) warm.push_back("ARNDCQEGHILKMFPSTWYV"[(i * 7) % 20]);
+            for (int rep = 0; rep < 2; rep++) {  // twice: the second pass runs with a measured SM partition
+                for (auto& sh : shards) enqueueScan(*sh, warm.data(), (int)warm.size(), std::min(k, kTopkMaxCandidates / 2));
+                for (auto& sh : shards) { SW4_CUDA(cudaSetDevice(sh->device)); SW4_CUDA(cudaStreamSynchronize(sh->stream)); updateClassRates(*sh); }
+            }
+            for (auto& sh : shards) { SW4_CUDA(cudaSetDevice(sh->device)); SW4_CUDA(cudaStreamSynchronize(sh->stream)); updateClassRates(*sh); }
         }
     }
 
@@ -476,6 +503,7 @@ struct Engine {
         SW4_CUDA(cudaMemcpyAsync(sh.dQueryLetters.p, sh.hQuery, (size_t)qlen, cudaMemcpyHostToDevice, st));
         SW4_CUDA(cudaMemcpyAsync(sh.dMatrix.p, matrix, 441, cudaMemcpyHostToDevice, st));
         SW4_CUDA(cudaMemsetAsync(sh.dCounters.p, 0, kNumCounters * sizeof(int), st));
+        SW4_CUDA(cudaMemsetAsync(sh.dClassNs.p, 0, 32 * sizeof(unsigned long long), st));
         if (qlen == 0) SW4_CUDA(cudaMemsetAsync(sh.dScores.p, 0, std::max<size_t>(sh.n, 1) * sizeof(int32_t), st));
         if (qpad > 0) convert_query_kernel<<<(qpad + 255) / 256, 256, 0, st>>>(sh.dQueryLetters.p, sh.dQueryCodes.p, qlen, qpad);
         build_profile_kernel<<<dim3((profStride + 127) / 128, kFused), 128, 0, st>>>(sh.dQueryCodes.p, qlen, sh.dMatrix.p,
@@ -487,10 +515,47 @@ struct Engine {
         // packed 16-bit classes, longest first
         const uint32_t gop2 = ((uint32_t)(uint16_t)(int16_t)gop << 16) | (uint16_t)(int16_t)gop;
         const uint32_t gex2 = ((uint32_t)(uint16_t)(int16_t)gex << 16) | (uint16_t)(int16_t)gex;
-        for (int ci = (int)sh.classes.size() - 1; ci >= 0 && qlen > 0; ci--) {
+        // All length classes run CONCURRENTLY, each on its own stream with its own share of the SMs (one persistent CTA
+        // per SM): the shares are sized so that every class finishes at about the same time, instead of 17 launches that
+        // each under-fill the GPU one after the other (the reference: 36 launches over 10 streams, src/cudasw4.cuh:1745).
+        const int numClasses = (int)sh.classes.size();
+        std::vector<int> grid(numClasses, 0), cap(numClasses, 0);
+        std::vector<double> cost(numClasses, 0.0);
+        if (qlen > 0 && numClasses > 0) {
+            int used = 0;
+            for (int ci = 0; ci < numClasses; ci++) {
+                const ClassLayout& cl = *sh.classes[ci];
+                const LengthClass& lc = kLengthClasses[cl.cls];
+                const int G = 1 << lc.logG;
+                const int groupsPerCta = kS16Warps * (32 >> lc.logG);
+                const int period = std::max(32, (qlen + G - 1 + 3) / 4 * 4);
+                cap[ci] = std::max(1, (cl.numItems + groupsPerCta - 1) / groupsPerCta);
+                cost[ci] = (double)cl.numBlocks / groupsPerCta * period * (lc.R * 7.3 + 30.0) * cl.rate;
+                grid[ci] = 1;
+                used++;
+            }
+            while (used < sh.smCount) {  // next SM goes to the class with the largest remaining load per SM
+                int best = -1;
+                double bestLoad = 0;
+                for (int ci = 0; ci < numClasses; ci++) {
+                    if (grid[ci] >= cap[ci]) continue;
+                    const double load = cost[ci] / grid[ci];
+                    if (load > bestLoad) { bestLoad = load; best = ci; }
+                }
+                if (best < 0) break;
+                grid[best]++;
+                used++;
+            }
+            SW4_CUDA(cudaEventRecord(sh.evFork, st));
+        }
+        for (int ci = numClasses - 1; ci >= 0 && qlen > 0; ci--) {
             ClassLayout& cl = *sh.classes[ci];
             const LengthClass& lc = kLengthClasses[cl.cls];
             const int G = 1 << lc.logG;
+            cudaStream_t cst = sh.classStreams[ci % kMaxClassStreams];
+            SW4_CUDA(cudaStreamWaitEvent(cst, sh.evFork, 0));
+            cl.lastCost = cost[ci] / cl.rate;
+            cl.lastGrid = grid[ci];
             S16Params prm{};
             prm.cols = cl.cols.p;
             prm.items = cl.items.p;
@@ -509,23 +574,24 @@ struct Engine {
             prm.ovfList = sh.dOvfList.p;
             prm.ovfCount = sh.dCounters.p + 0;
             prm.statCount = sh.dCounters.p + 1;
+            prm.elapsedNs = sh.dClassNs.p + cl.cls;
             prm.border = sh.dBorder16.p;
             prm.borderStride = (int)sh.border16Stride;
-            const int groupsPerCta = kS16Warps * (32 >> lc.logG);
-            const int grid = std::max(1, std::min(sh.smCount, (cl.numItems + groupsPerCta - 1) / groupsPerCta));
             if (lc.multi) {
-                launch_s16<32, true>(prm, grid, st);
+                launch_s16<32, true>(prm, grid[ci], cst);
             } else {
                 switch (lc.R) {
-                    case 8: launch_s16<8, false>(prm, grid, st); break;
-                    case 16: launch_s16<16, false>(prm, grid, st); break;
-                    case 20: launch_s16<20, false>(prm, grid, st); break;
-                    case 24: launch_s16<24, false>(prm, grid, st); break;
-                    case 28: launch_s16<28, false>(prm, grid, st); break;
-                    case 32: launch_s16<32, false>(prm, grid, st); break;
+                    case 8: launch_s16<8, false>(prm, grid[ci], cst); break;
+                    case 16: launch_s16<16, false>(prm, grid[ci], cst); break;
+                    case 20: launch_s16<20, false>(prm, grid[ci], cst); break;
+                    case 24: launch_s16<24, false>(prm, grid[ci], cst); break;
+                    case 28: launch_s16<28, false>(prm, grid[ci], cst); break;
+                    case 32: launch_s16<32, false>(prm, grid[ci], cst); break;
                     default: fail(SW4_ERR_INVALID, "no kernel for R=%d", lc.R);
                 }
             }
+            SW4_CUDA(cudaEventRecord(sh.evJoin[ci % kMaxClassStreams], cst));
+            SW4_CUDA(cudaStreamWaitEvent(st, sh.evJoin[ci % kMaxClassStreams], 0));
             sh.launches++;
         }
 
@@ -573,7 +639,30 @@ struct Engine {
             SW4_CUDA(cudaMemcpyAsync(sh.hTop + k, sh.dTopIds.p, (size_t)k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         }
         SW4_CUDA(cudaMemcpyAsync(sh.hTop + 2 * k, sh.dCounters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        SW4_CUDA(cudaMemcpyAsync(sh.hClassNs, sh.dClassNs.p, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         SW4_CUDA(cudaEventRecord(sh.evStop, st));
+    }
+
+    // feedback for the SM partition: how many SM-milliseconds a unit of modelled cost really took in the last scan
+    static void updateClassRates(Shard& sh) {
+        double norm = 0;
+        int cnt = 0;
+        for (auto& clp : sh.classes) {
+            ClassLayout& cl = *clp;
+            if (cl.lastGrid == 0 || cl.lastCost <= 0 || !sh.hClassNs) continue;
+            const double ms = (double)sh.hClassNs[cl.cls] * 1e-6;
+            if (ms <= 0) continue;
+            const double r = (double)ms * cl.lastGrid / cl.lastCost;
+            if (getenv("SW4_DEBUG_PARTITION"))
+                fprintf(stderr, "[sw4] class %2d (G=%2d R=%2d%s) items %7d blocks %7d grid %3d  %.3f ms  rate %.4g -> %.4g\n", cl.cls,
+                        1 << kLengthClasses[cl.cls].logG, kLengthClasses[cl.cls].R, kLengthClasses[cl.cls].multi ? " multi" : "",
+                        cl.numItems, cl.numBlocks, cl.lastGrid, ms, cl.rate, r);
+            cl.rate = (cl.rate == 1.0) ? r : 0.5 * cl.rate + 0.5 * r;
+            cl.lastGrid = 0;
+            norm += cl.rate;
+            cnt++;
+        }
+        (void)norm; (void)cnt;
     }
 
     void scan(const char* query, int qlen, int32_t* outScores, int32_t* outIds, int32_t* outCount, sw4_stats* stats) {
@@ -595,6 +684,7 @@ struct Engine {
             SW4_CUDA(cudaSetDevice(sh.device));
             SW4_CUDA(cudaStreamSynchronize(sh.stream));
             float ms = 0, kms = 0;
+            updateClassRates(sh);
             SW4_CUDA(cudaEventElapsedTime(&ms, sh.evStart, sh.evStop));
             SW4_CUDA(cudaEventElapsedTime(&kms, sh.evK0, sh.evK1));
             seconds = std::max(seconds, (double)ms * 1e-3);

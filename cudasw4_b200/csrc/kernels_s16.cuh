@@ -63,6 +63,7 @@ struct S16Params {
     int32_t* ovfList;            // local subject indices that need the exact 32-bit path
     int* ovfCount;
     int* statCount;
+    unsigned long long* elapsedNs;  // max over CTAs of this launch's run time (feedback for the host's SM partition)
     uint2* border;               // MULTI only: [gridWarps][borderStride] (H, E) of a segment's last column per query row
     int borderStride;
 };
@@ -120,6 +121,8 @@ template <int R, bool MULTI>
 __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params prm) {
     static_assert(R % 4 == 0, "a lane's staging slice (R u16 codes) must be a whole number of 8-byte chunks");
     extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long tStart;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tStart));
     const uint32_t ringBase = (uint32_t)__cvta_generic_to_shared(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int logG = MULTI ? 5 : prm.logG, G = 1 << logG;
@@ -315,6 +318,11 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
             }
             if (++p == P) p = 0;
         });
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long tEnd;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tEnd));
+        atomicMax(prm.elapsedNs, tEnd - tStart);
     }
 }
 
