@@ -66,7 +66,7 @@ struct Error {
 // long class: subjects longer than 1024 are cut into segments of 1024 columns that one warp aligns back to back.
 struct LengthClass { int logG, R, capacity; bool multi; };
 static const LengthClass kLengthClasses[] = {
-    {2, 8, 32, false},    {2, 16, 64, false},   {2, 24, 96, false},   {2, 32, 128, false},  {3, 20, 160, false},
+    {3, 4, 32, false},    {3, 8, 64, false},    {3, 12, 96, false},   {3, 16, 128, false},  {3, 20, 160, false},
     {3, 24, 192, false},  {3, 28, 224, false},  {3, 32, 256, false},  {4, 20, 320, false},  {4, 24, 384, false},
     {4, 28, 448, false},  {4, 32, 512, false},  {5, 20, 640, false},  {5, 24, 768, false},  {5, 28, 896, false},
     {5, 32, 1024, false}, {5, 32, 1024, true},
@@ -175,8 +175,8 @@ struct Shard {
     int smCount = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t evStart = nullptr, evK0 = nullptr, evK1 = nullptr, evStop = nullptr, evFork = nullptr;
-    cudaStream_t classStreams[kMaxClassStreams] = {};
-    cudaEvent_t evJoin[kMaxClassStreams] = {};
+    cudaStream_t classStreams[kMaxClassStreams] = {}, oddStreams[kMaxClassStreams] = {};
+    cudaEvent_t evJoin[kMaxClassStreams] = {}, evJoinOdd[kMaxClassStreams] = {};
     // subject selection
     std::vector<int32_t> globalIds;  // local index -> global id (ascending)
     uint64_t residues = 0;
@@ -189,6 +189,7 @@ struct Shard {
     std::vector<std::unique_ptr<ClassLayout>> classes;
     DevBuf<int32_t> dLongList;  // subjects beyond the s16 tile, ascending length
     int numLong = 0;
+    size_t numZeroLength = 0;  // the shard's first entries (it is sorted by length)
     // per scan
     DevBuf<int32_t> dScores, dOvfList;
     DevBuf<int> dCounters;  // [0] overflow count, [1] stat count, [2] ticket long, [3] ticket overflow, [4] topk count
@@ -222,7 +223,9 @@ struct Shard {
         if (evFork) cudaEventDestroy(evFork);
         for (int i = 0; i < kMaxClassStreams; i++) {
             if (evJoin[i]) cudaEventDestroy(evJoin[i]);
+            if (evJoinOdd[i]) cudaEventDestroy(evJoinOdd[i]);
             if (classStreams[i]) cudaStreamDestroy(classStreams[i]);
+            if (oddStreams[i]) cudaStreamDestroy(oddStreams[i]);
         }
         if (stream) cudaStreamDestroy(stream);
     }
@@ -237,8 +240,21 @@ static void launch_s16(const S16Params& prm, int grid, cudaStream_t stream) {
         SW4_CUDA(cudaFuncSetAttribute(sw_s16_kernel<R, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16_smem_bytes<R>()));
         configured[dev & 63] = true;
     }
-    sw_s16_kernel<R, MULTI><<<grid, kS16Threads, s16_smem_bytes<R>(), stream>>>(prm);
-    SW4_CUDA(cudaGetLastError());
+    // CTAs are launched as clusters of 2 whenever the grid is even: the two SMs of a TPC share an instruction cache, and
+    // with 17 different (large, heavily unrolled) kernels resident at once it pays to give both SMs the same code.
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kS16Threads);
+    cfg.dynamicSmemBytes = s16_smem_bytes<R>();
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (grid % 2 == 0 && !getenv("SW4_NO_CLUSTER")) ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SW4_CUDA(cudaLaunchKernelEx(&cfg, sw_s16_kernel<R, MULTI>, prm));
 }
 
 struct Engine {
@@ -315,7 +331,9 @@ struct Engine {
             SW4_CUDA(cudaEventCreateWithFlags(&sh.evFork, cudaEventDisableTiming));
             for (int i = 0; i < kMaxClassStreams; i++) {
                 SW4_CUDA(cudaStreamCreateWithFlags(&sh.classStreams[i], cudaStreamNonBlocking));
+                SW4_CUDA(cudaStreamCreateWithFlags(&sh.oddStreams[i], cudaStreamNonBlocking));
                 SW4_CUDA(cudaEventCreateWithFlags(&sh.evJoin[i], cudaEventDisableTiming));
+                SW4_CUDA(cudaEventCreateWithFlags(&sh.evJoinOdd[i], cudaEventDisableTiming));
             }
         }
     }
@@ -377,6 +395,7 @@ struct Engine {
         // length classes (the shard is ascending in length): consecutive subjects are paired into work items
         sh.classes.clear();
         size_t pos = std::upper_bound(lengths.begin(), lengths.end(), 0) - lengths.begin();  // length-0 subjects score 0
+        sh.numZeroLength = pos;
         std::vector<S16Item> items;
         std::vector<int32_t> blockItem;
         for (int c = 0; c < kNumLengthClasses; c++) {
@@ -504,7 +523,10 @@ struct Engine {
         SW4_CUDA(cudaMemcpyAsync(sh.dMatrix.p, matrix, 441, cudaMemcpyHostToDevice, st));
         SW4_CUDA(cudaMemsetAsync(sh.dCounters.p, 0, kNumCounters * sizeof(int), st));
         SW4_CUDA(cudaMemsetAsync(sh.dClassNs.p, 0, 32 * sizeof(unsigned long long), st));
-        if (qlen == 0) SW4_CUDA(cudaMemsetAsync(sh.dScores.p, 0, std::max<size_t>(sh.n, 1) * sizeof(int32_t), st));
+        // every scan starts from "-1 = not scored" so that a subject the kernels missed can never keep an old score;
+        // empty subjects (and everything, for an empty query) score 0 by definition
+        SW4_CUDA(cudaMemsetAsync(sh.dScores.p, qlen == 0 ? 0 : 0xff, std::max<size_t>(sh.n, 1) * sizeof(int32_t), st));
+        if (qlen > 0 && sh.numZeroLength) SW4_CUDA(cudaMemsetAsync(sh.dScores.p, 0, sh.numZeroLength * sizeof(int32_t), st));
         if (qpad > 0) convert_query_kernel<<<(qpad + 255) / 256, 256, 0, st>>>(sh.dQueryLetters.p, sh.dQueryCodes.p, qlen, qpad);
         build_profile_kernel<<<dim3((profStride + 127) / 128, kFused), 128, 0, st>>>(sh.dQueryCodes.p, qlen, sh.dMatrix.p,
                                                                                    sh.dProfile.p, profStride);
@@ -528,7 +550,7 @@ struct Engine {
                 const LengthClass& lc = kLengthClasses[cl.cls];
                 const int G = 1 << lc.logG;
                 const int groupsPerCta = kS16Warps * (32 >> lc.logG);
-                const int period = std::max(32, (qlen + G - 1 + 3) / 4 * 4);
+                const int period = std::max(32, (qlen + G - 1 + 7) / 8 * 8);
                 cap[ci] = std::max(1, (cl.numItems + groupsPerCta - 1) / groupsPerCta);
                 cost[ci] = (double)cl.numBlocks / groupsPerCta * period * (lc.R * 7.3 + 30.0) * cl.rate;
                 grid[ci] = 1;
@@ -565,7 +587,7 @@ struct Engine {
             prm.profile = sh.dProfile.p;
             prm.profStride = profStride;
             prm.qlen = qlen;
-            prm.period = std::max(32, (qlen + G - 1 + 3) / 4 * 4);  // >= 32 so that no lane starts before step 0
+            prm.period = std::max(32, (qlen + G - 1 + 7) / 8 * 8);  // >= 32 so that no lane starts before step 0
             prm.gop2 = gop2;
             prm.gex2 = gex2;
             prm.ovfThreshold = kS16OverflowThreshold;
@@ -577,22 +599,38 @@ struct Engine {
             prm.elapsedNs = sh.dClassNs.p + cl.cls;
             prm.border = sh.dBorder16.p;
             prm.borderStride = (int)sh.border16Stride;
-            if (lc.multi) {
-                launch_s16<32, true>(prm, grid[ci], cst);
-            } else {
-                switch (lc.R) {
-                    case 8: launch_s16<8, false>(prm, grid[ci], cst); break;
-                    case 16: launch_s16<16, false>(prm, grid[ci], cst); break;
-                    case 20: launch_s16<20, false>(prm, grid[ci], cst); break;
-                    case 24: launch_s16<24, false>(prm, grid[ci], cst); break;
-                    case 28: launch_s16<28, false>(prm, grid[ci], cst); break;
-                    case 32: launch_s16<32, false>(prm, grid[ci], cst); break;
-                    default: fail(SW4_ERR_INVALID, "no kernel for R=%d", lc.R);
+            auto launchClass = [&](int g, cudaStream_t strm, int ctaOffset) {
+                prm.ctaOffset = ctaOffset;
+                if (lc.multi) {
+                    launch_s16<32, true>(prm, g, strm);
+                } else {
+                    switch (lc.R) {
+                        case 4: launch_s16<4, false>(prm, g, strm); break;
+                        case 8: launch_s16<8, false>(prm, g, strm); break;
+                        case 12: launch_s16<12, false>(prm, g, strm); break;
+                        case 16: launch_s16<16, false>(prm, g, strm); break;
+                        case 20: launch_s16<20, false>(prm, g, strm); break;
+                        case 24: launch_s16<24, false>(prm, g, strm); break;
+                        case 28: launch_s16<28, false>(prm, g, strm); break;
+                        case 32: launch_s16<32, false>(prm, g, strm); break;
+                        default: fail(SW4_ERR_INVALID, "no kernel for R=%d", lc.R);
+                    }
                 }
-            }
+                sh.launches++;
+            };
+            // even part as clusters of 2 (same code on both SMs of a TPC), an odd leftover CTA on a second stream;
+            // both launches share the class's ticket counter and timing slot
+            const int evenPart = grid[ci] & ~1;
+            if (evenPart > 0) launchClass(evenPart, cst, 0);
             SW4_CUDA(cudaEventRecord(sh.evJoin[ci % kMaxClassStreams], cst));
             SW4_CUDA(cudaStreamWaitEvent(st, sh.evJoin[ci % kMaxClassStreams], 0));
-            sh.launches++;
+            if (grid[ci] & 1) {
+                cudaStream_t ost = sh.oddStreams[ci % kMaxClassStreams];
+                SW4_CUDA(cudaStreamWaitEvent(ost, sh.evFork, 0));
+                launchClass(1, ost, evenPart);
+                SW4_CUDA(cudaEventRecord(sh.evJoinOdd[ci % kMaxClassStreams], ost));
+                SW4_CUDA(cudaStreamWaitEvent(st, sh.evJoinOdd[ci % kMaxClassStreams], 0));
+            }
         }
 
         // exact 32-bit path: long subjects, then whatever saturated in 16 bit

@@ -55,7 +55,7 @@ struct S16Params {
     const uint32_t* profile;     // [441][profStride] positional query profile
     int profStride;
     int qlen;
-    int period;                  // P: steps between two alignments of a group; multiple of 4, >= max(32, qlen + G - 1)
+    int period;                  // P: steps between two alignments of a group; multiple of 8, >= max(32, qlen + G - 1); G >= 8
     uint32_t gop2, gex2;         // gap scores replicated in both halves
     int ovfThreshold;            // running maximum >= this => exact 32-bit re-scoring (25000, reference MAX_ACC_SHORT)
     int statThreshold;           // running maximum >= this => counted in stats.num_overflows (25000, or 2048 for Half2)
@@ -64,6 +64,7 @@ struct S16Params {
     int* ovfCount;
     int* statCount;
     unsigned long long* elapsedNs;  // max over CTAs of this launch's run time (feedback for the host's SM partition)
+    int ctaOffset;               // index of this launch's first CTA within the class (a class may be split in two launches)
     uint2* border;               // MULTI only: [gridWarps][borderStride] (H, E) of a segment's last column per query row
     int borderStride;
 };
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
     // [3] look-ahead valid [4] look-ahead block [5] look-ahead starts a new item [6] look-ahead item index
     volatile int* gs = reinterpret_cast<volatile int*>(smem + kRingBytes + kS16Warps * 32 * R * 2) +
                        (warp * 8 + g) * kGroupStateInts;
-    uint2* border = MULTI ? prm.border + (size_t)(blockIdx.x * kS16Warps + warp) * prm.borderStride : nullptr;
+    uint2* border = MULTI ? prm.border + (size_t)((blockIdx.x + prm.ctaOffset) * kS16Warps + warp) * prm.borderStride : nullptr;
 
     uint32_t colAddr[R];  // ring byte address of this column's fused-pair row (lane and batch-phase offsets folded in)
     uint32_t Hp[R];       // H of the previous row
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
         }
         static_for<kFillBatch>([&](auto stepIndex) {
             constexpr int i = decltype(stepIndex)::value;
-            if ((i & 3) == 0 && p == pRestart && alive) {  // group restart: uniform in the group, divergent across groups
+            if ((i & 7) == 0 && p == pRestart && alive) {  // group restart: uniform in the group, divergent across groups
                 __syncwarp(groupMask);
                 int segsLeft = gs[2];
                 if (haveWork && segsLeft == 0) {  // the item is complete: reduce the maxima and store the two scores

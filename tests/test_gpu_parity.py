@@ -139,6 +139,30 @@ def test_scores_beyond_16_bit_are_exact(oracle):
             assert res.scores == s.tolist() and res.referenceIds == i.tolist()
 
 
+def test_many_long_subjects_repeated_scans(oracle):
+    """Enough multi-segment subjects to spread the long class over many (and an odd number of) SMs, scanned several
+    times with different queries: every score must match the oracle every time (no stale or shared border state)."""
+    rng = np.random.default_rng(21)
+    L = np.concatenate([rng.integers(1025, 3200, 2300), rng.integers(60, 900, 800)])
+    seqs = [synth.random_residues(rng, int(n)) for n in L]
+    qs = [synth.random_residues(rng, n) for n in (97, 310, 150)]
+    seqs += [np.concatenate([q, synth.random_residues(rng, 1500)]) for q in qs]
+    db = dbformat.from_sequences(seqs)
+    with _engine(numTop=10, blosumType=62) as eng:
+        eng.setDatabase(db)
+        for rep in range(2):
+            for q in qs:
+                res = eng.scan(dbformat.decode(q))
+                scores, ids = eng.lastScanAllScores()
+                got = np.empty(db.num_sequences, np.int32)
+                got[ids] = scores
+                ref = oracle.scan(62, q, db, -11, -1)
+                bad = np.nonzero(got != ref)[0]
+                assert len(bad) == 0, (rep, len(q), bad[:8], got[bad[:8]], ref[bad[:8]], db.lengths[bad[:8]])
+                s, i = oracle.topk(ref, 10)
+                assert res.scores == s.tolist() and res.referenceIds == i.tolist()
+
+
 def test_edge_cases(oracle):
     rng = np.random.default_rng(3)
     seqs = [np.zeros(0, np.uint8), np.zeros(0, np.uint8), synth.random_residues(rng, 1), synth.random_residues(rng, 5)]

@@ -16,3 +16,11 @@ with sw.CudaSW4(deviceIds=[0], numTop=10, blosumType=62, verbose=True) as eng:
         for _ in range(reps):
             r = eng.scan(queries[qi][1])
         print(f"q{qi} len {len(queries[qi][1])}: {r.stats.gcups:.1f} GCUPS kernel-only {r.stats.cells/1e9/r.stats.kernelSeconds:.1f} launches {r.stats.kernelLaunches} ovf {r.stats.numOverflows}", flush=True)
+    if os.environ.get("C3_CHECK"):
+        from tests import oracle_lib
+        orc = oracle_lib.load()
+        for qi in qsel:
+            q = dbformat.encode(queries[qi][1])
+            r = eng.scan(queries[qi][1])
+            ref = [orc.score(62, q, db.sequence(i), -11, -1) for i in r.referenceIds]
+            print("check q", qi, "scores", r.scores, "oracle", ref, "ovf", r.stats.numOverflows, "lens", [int(db.lengths[i]) for i in r.referenceIds], flush=True)
