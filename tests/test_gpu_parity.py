@@ -212,6 +212,26 @@ def test_shards_partition_the_database(oracle):
     assert [m[0] for m in merged[:15]] == s.tolist() and [m[1] for m in merged[:15]] == i.tolist()
 
 
+def test_in_process_multi_gpu(oracle):
+    """All visible GPUs driven from one handle, like the reference's single process (skipped on a 1-GPU box)."""
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    db, rng = _mixed_db(31, 6000, 10, 1400, [2500, 5000])
+    qs = [synth.random_residues(rng, n) for n in (200, 431)]
+    with sw.CudaSW4(deviceIds=list(range(ngpu)), numTop=20, blosumType=62) as eng:
+        eng.setDatabase(db)
+        for q in qs:
+            res = eng.scan(dbformat.decode(q))
+            scores, ids = eng.lastScanAllScores()
+            assert sorted(ids.tolist()) == list(range(db.num_sequences))
+            ref = oracle.scan(62, q, db, -11, -1)
+            assert (scores == ref[ids]).all()
+            s, i = oracle.topk(ref, 20)
+            assert res.scores == s.tolist() and res.referenceIds == i.tolist()
+
+
 def test_full_size_peak_config_properties():
     """BASELINE config[1] at full size (1M x 256): every subject is identical, so every score must equal the known
     answer, the checksum of scores is n * answer, and top-10 ids are 0..9."""
