@@ -10,7 +10,6 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
-#include <mutex>
 #include <random>
 #include <string>
 #include <thread>
@@ -35,8 +34,6 @@ namespace sw4 {
 // ---------------------------------------------------------------------------------------------------------------
 // errors
 // ---------------------------------------------------------------------------------------------------------------
-static thread_local std::string g_lastError;
-
 struct Error {
     int code;
     std::string msg;
@@ -72,7 +69,6 @@ static const LengthClass kLengthClasses[] = {
     {5, 32, 1024, false}, {5, 32, 1024, true},
 };
 constexpr int kNumLengthClasses = sizeof(kLengthClasses) / sizeof(kLengthClasses[0]);
-constexpr int kMaxS16Length = 1024;
 constexpr int kS16OverflowThreshold = 25000;  // reference MAX_ACC_SHORT, src/kernels.cuh:5
 constexpr int kHalf2Threshold = 2048;         // reference MAX_ACC_HALF2, src/kernels.cuh:4
 constexpr int kNumCounters = 8 + 32;           // [0] overflow [1] stat [2],[3] s32 tickets [4] top-k count [8+c] class tickets
@@ -187,8 +183,6 @@ struct Shard {
     DevBuf<size_t> dOffsets;
     DevBuf<int32_t> dLengths, dGlobalIds;
     std::vector<std::unique_ptr<ClassLayout>> classes;
-    DevBuf<int32_t> dLongList;  // subjects beyond the s16 tile, ascending length
-    int numLong = 0;
     size_t numZeroLength = 0;  // the shard's first entries (it is sorted by length)
     // per scan
     DevBuf<int32_t> dScores, dOvfList;
@@ -443,13 +437,11 @@ struct Engine {
             }
             pos = std::max(pos, end);
         }
-        sh.numLong = 0;
-        sh.dLongList.alloc(1);
         SW4_CUDA(cudaStreamSynchronize(sh.stream));
         sh.uploaded = true;
         if (verbose)
-            fprintf(stderr, "[sw4] device %d: %zu subjects, %llu residues, %zu length classes, %d long subjects\n", sh.device,
-                    n, (unsigned long long)sh.residues, sh.classes.size(), sh.numLong);
+            fprintf(stderr, "[sw4] device %d: %zu subjects, %llu residues, %zu length classes\n", sh.device, n,
+                    (unsigned long long)sh.residues, sh.classes.size());
     }
 
     void upload() {
@@ -650,7 +642,6 @@ struct Engine {
             sh.launches++;
         };
         if (qlen > 0) {
-            if (sh.numLong > 0) launchS32(sh.dLongList.p, nullptr, sh.numLong, sh.dCounters.p + 2, true);
             if (!sh.classes.empty()) launchS32(sh.dOvfList.p, sh.dCounters.p + 0, 0, sh.dCounters.p + 3, false);
         }
         SW4_CUDA(cudaEventRecord(sh.evK1, st));
@@ -711,8 +702,10 @@ struct Engine {
         upload();
         const size_t nTotal = db->n;
         const int k = (int)std::min<size_t>((size_t)std::max(numTop, 0), nTotal);
-        if (k > kTopkMaxCandidates / 2) fail(SW4_ERR_INVALID, "num_top %d exceeds the supported maximum %d", k, kTopkMaxCandidates / 2);
-        for (auto& sh : shards) enqueueScan(*sh, query, qlen, k);
+        // Result lists longer than the device selection keeps (4096) are rare (the reference's CLI default is 10): they take
+        // the slow but exact route of copying all scores to the host (the reference's CUDASW_DEBUG_CHECK_CORRECTNESS mode).
+        const bool hostSelect = k > kTopkMaxCandidates / 2;
+        for (auto& sh : shards) enqueueScan(*sh, query, qlen, hostSelect ? 0 : k);
         double seconds = 0, kernelSeconds = 0;
         int overflows = 0, launches = 0;
         struct Entry { int32_t score, id; };
@@ -727,17 +720,24 @@ struct Engine {
             SW4_CUDA(cudaEventElapsedTime(&kms, sh.evK0, sh.evK1));
             seconds = std::max(seconds, (double)ms * 1e-3);
             kernelSeconds = std::max(kernelSeconds, (double)kms * 1e-3);
-            const int* counters = sh.hTop + 2 * k;
+            const int kDev = hostSelect ? 0 : k;
+            const int* counters = sh.hTop + 2 * kDev;
             overflows += counters[1];
             launches += sh.launches;
-            const int cnt = (k > 0 && sh.n > 0) ? counters[4] : 0;
-            for (int i = 0; i < cnt; i++) merged.push_back(Entry{sh.hTop[i], sh.hTop[k + i]});
+            if (hostSelect) {
+                std::vector<int32_t> all(sh.n);
+                SW4_CUDA(cudaMemcpy(all.data(), sh.dScores.p, sh.n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+                for (size_t i = 0; i < sh.n; i++) merged.push_back(Entry{all[i], sh.globalIds[i]});
+            } else {
+                const int cnt = (k > 0 && sh.n > 0) ? counters[4] : 0;
+                for (int i = 0; i < cnt; i++) merged.push_back(Entry{sh.hTop[i], sh.hTop[k + i]});
+            }
         }
-        std::sort(merged.begin(), merged.end(), [](const Entry& a, const Entry& b) {
+        const int got = (int)std::min<size_t>((size_t)k, merged.size());
+        std::partial_sort(merged.begin(), merged.begin() + got, merged.end(), [](const Entry& a, const Entry& b) {
             if (a.score != b.score) return a.score > b.score;
             return a.id < b.id;
         });
-        const int got = (int)std::min<size_t>((size_t)k, merged.size());
         for (int i = 0; i < got; i++) { outScores[i] = merged[i].score; outIds[i] = merged[i].id; }
         if (outCount) *outCount = got;
         uint64_t residues = 0;

@@ -77,7 +77,7 @@ inline PseudoDB loadPseudoDB(size_t num, SequenceLengthT length, int randomseed 
 class CudaSW4 {
 public:
     CudaSW4(std::vector<int> deviceIds_, int numTop_, BlosumType blosumType, const KernelTypeConfig& kernelTypeConfig,
-            const MemoryConfig& memoryConfig, bool verbose_) : verbose(verbose_) {                    // :496-531
+            const MemoryConfig& memoryConfig, bool verbose_) : numTop(numTop_), verbose(verbose_) {                    // :496-531
         sw4_mem_config mem{memoryConfig.maxBatchBytes, memoryConfig.maxBatchSequences, memoryConfig.maxTempBytes,
                            memoryConfig.maxGpuMem};
         const int rc = sw4_create(deviceIds_.data(), (int)deviceIds_.size(), numTop_, blosumNumber(blosumType), gop, gex,
@@ -87,9 +87,9 @@ public:
     }
     CudaSW4() = delete;
     CudaSW4(const CudaSW4&) = delete;
-    CudaSW4(CudaSW4&& o) noexcept : handle(o.handle), gop(o.gop), gex(o.gex), verbose(o.verbose) { o.handle = nullptr; }
+    CudaSW4(CudaSW4&& o) noexcept : handle(o.handle), numTop(o.numTop), gop(o.gop), gex(o.gex), verbose(o.verbose) { o.handle = nullptr; }
     CudaSW4& operator=(const CudaSW4&) = delete;
-    CudaSW4& operator=(CudaSW4&& o) noexcept { std::swap(handle, o.handle); gop = o.gop; gex = o.gex; return *this; }
+    CudaSW4& operator=(CudaSW4&& o) noexcept { std::swap(handle, o.handle); numTop = o.numTop; gop = o.gop; gex = o.gex; return *this; }
     ~CudaSW4() { if (handle) sw4_destroy(handle); }
 
     void setGapOpenScore(int score) {                                                                 // :539-544
@@ -111,7 +111,7 @@ public:
         check(sw4_set_pseudo_database(handle, db->num, db->length, db->randomseed));
     }
     void setBlosum(BlosumType blosumType) { check(sw4_set_blosum(handle, blosumNumber(blosumType))); } // :570
-    void setNumTop(int value) { if (value >= 0) check(sw4_set_num_top(handle, value)); }              // :574
+    void setNumTop(int value) { if (value >= 0) { check(sw4_set_num_top(handle, value)); numTop = value; } }              // :574
     void setKernelTypeConfig(const KernelTypeConfig& val) {                                           // :589-607
         check(sw4_set_kernel_types(handle, (int)val.singlePassType, (int)val.manyPassType_small, (int)val.manyPassType_large,
                                    (int)val.overflowType));
@@ -136,7 +136,8 @@ public:
         sw4_db_info info{};
         check(sw4_get_db_info(handle, &info));
         ScanResult result;
-        std::vector<int32_t> scores(maxResults(info)), ids(maxResults(info));
+        const size_t cap = (size_t)std::max<uint64_t>(1, std::min<uint64_t>(info.num_sequences, (uint64_t)std::max(numTop, 0)));
+        std::vector<int32_t> scores(cap), ids(cap);
         int32_t count = 0; sw4_stats st{};
         check(sw4_scan(handle, query, queryLength, scores.data(), ids.data(), &count, &st));
         result.scores.assign(scores.begin(), scores.begin() + count);
@@ -168,9 +169,9 @@ public:
     sw4_handle* nativeHandle() const { return handle; }
 
 private:
-    static size_t maxResults(const sw4_db_info& info) { return (size_t)std::max<uint64_t>(1, std::min<uint64_t>(info.num_sequences, 4096)); }
     void check(int rc) const { if (rc != SW4_OK) throw std::runtime_error(sw4_last_error(handle)); }
     sw4_handle* handle = nullptr;
+    int numTop = 10;
     int gop = -11, gex = -1;                                                                          // :2443-2444
     bool verbose = false;
 };

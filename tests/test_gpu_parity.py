@@ -163,6 +163,19 @@ def test_many_long_subjects_repeated_scans(oracle):
                 assert res.scores == s.tolist() and res.referenceIds == i.tolist()
 
 
+def test_large_top_k_uses_exact_host_selection(oracle):
+    db, rng = _mixed_db(55, 7000, 20, 300)
+    q = synth.random_residues(rng, 180)
+    ref = oracle.scan(62, q, db, -11, -1)
+    for k in (4096, 5000, 100000):
+        with _engine(numTop=k, blosumType=62) as eng:
+            eng.setDatabase(db)
+            res = eng.scan(dbformat.decode(q))
+            s, i = oracle.topk(ref, k)
+            assert len(res.scores) == min(k, db.num_sequences)
+            assert res.scores == s.tolist() and res.referenceIds == i.tolist()
+
+
 def test_edge_cases(oracle):
     rng = np.random.default_rng(3)
     seqs = [np.zeros(0, np.uint8), np.zeros(0, np.uint8), synth.random_residues(rng, 1), synth.random_residues(rng, 5)]
