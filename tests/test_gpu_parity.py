@@ -163,6 +163,29 @@ def test_many_long_subjects_repeated_scans(oracle):
                 assert res.scores == s.tolist() and res.referenceIds == i.tolist()
 
 
+def test_reconfigure_between_scans_and_empty_database(oracle):
+    """One handle, settings changed between scans (matrix, gaps, top-k, database) like the reference's setters allow."""
+    db, rng = _mixed_db(91, 900, 5, 700, [1500])
+    q = synth.random_residues(rng, 256)
+    with _engine(numTop=5, blosumType=62) as eng:
+        eng.setDatabase(db)
+        for blosum, gop, gex, k in ((62, -11, -1, 5), (45, -13, -2, 12), (80, -10, -1, 3), (50, -20, -5, 7)):
+            eng.setBlosum(blosum)
+            eng.setGapScores(gop, gex)
+            eng.setNumTop(k)
+            res = eng.scan(dbformat.decode(q))
+            s, i = oracle.topk(oracle.scan(blosum, q, db, gop, gex), k)
+            assert res.scores == s.tolist() and res.referenceIds == i.tolist(), (blosum, gop, gex)
+        db2, _ = _mixed_db(92, 300, 30, 90)
+        eng.setDatabase(db2)  # replaces the resident database
+        res = eng.scan(dbformat.decode(q))
+        s, i = oracle.topk(oracle.scan(50, q, db2, -20, -5), 7)
+        assert res.scores == s.tolist() and res.referenceIds == i.tolist()
+        eng.setDatabase(dbformat.from_sequences([]))
+        res = eng.scan(dbformat.decode(q))
+        assert res.scores == [] and res.referenceIds == []
+
+
 def test_large_top_k_uses_exact_host_selection(oracle):
     db, rng = _mixed_db(55, 7000, 20, 300)
     q = synth.random_residues(rng, 180)
