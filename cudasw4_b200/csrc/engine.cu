@@ -543,7 +543,8 @@ struct Engine {
                 const int G = 1 << lc.logG;
                 const int groupsPerCta = kS16Warps * (32 >> lc.logG);
                 const int period = std::max(32, (qlen + G - 1 + 7) / 8 * 8);
-                cap[ci] = std::max(1, (cl.numItems + groupsPerCta - 1) / groupsPerCta);
+                // a class may spread out to as few as 4 busy warps per SM (one per scheduler) when there are SMs to spare
+                cap[ci] = std::max(1, (cl.numItems + 3) / 4);
                 cost[ci] = (double)cl.numBlocks / groupsPerCta * period * (lc.R * 7.3 + 30.0) * cl.rate;
                 grid[ci] = 1;
                 used++;
@@ -589,6 +590,10 @@ struct Engine {
             prm.ovfCount = sh.dCounters.p + 0;
             prm.statCount = sh.dCounters.p + 1;
             prm.elapsedNs = sh.dClassNs.p + cl.cls;
+            {
+                const int groupsPerCta = kS16Warps * (32 >> lc.logG);
+                prm.activeGroups = std::min(groupsPerCta, std::max(1, (cl.numItems + grid[ci] - 1) / grid[ci]));
+            }
             prm.border = sh.dBorder16.p;
             prm.borderStride = (int)sh.border16Stride;
             auto launchClass = [&](int g, cudaStream_t strm, int ctaOffset) {

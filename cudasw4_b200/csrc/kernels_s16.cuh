@@ -64,6 +64,8 @@ struct S16Params {
     int* ovfCount;
     int* statCount;
     unsigned long long* elapsedNs;  // max over CTAs of this launch's run time (feedback for the host's SM partition)
+    int activeGroups;            // groups per CTA that take work (fewer than all when the class cannot fill its SMs: the
+                                 // items are then spread over more SMs and every warp gets a larger share of its scheduler)
     int ctaOffset;               // index of this launch's first CTA within the class (a class may be split in two launches)
     uint2* border;               // MULTI only: [gridWarps][borderStride] (H, E) of a segment's last column per query row
     int borderStride;
@@ -140,6 +142,26 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
                        (warp * 8 + g) * kGroupStateInts;
     uint2* border = MULTI ? prm.border + (size_t)((blockIdx.x + prm.ctaOffset) * kS16Warps + warp) * prm.borderStride : nullptr;
 
+    // Warps that will never get work (the class was spread over more SMs than it can fill, prm.activeGroups) only keep
+    // the CTA's ring going: same barriers and their share of every refill, none of the arithmetic, so the busy warps get
+    // their scheduler to themselves.
+    if (warp * (32 >> logG) >= prm.activeGroups) {
+        const uint32_t NEG2i = ((uint32_t)(uint16_t)kNegS16 << 16) | (uint16_t)kNegS16;
+        for (int i = threadIdx.x; i < kFused * kRingStride; i += kS16Threads) reinterpret_cast<uint32_t*>(smem)[i] = NEG2i;
+        __syncthreads();
+        ring_fill(ringBase, prm.profile, prm.profStride, 0, 0, P);
+        int pf = kFillBatch % P;
+#pragma unroll 1
+        for (int batch = 0;; ++batch) {
+            cp_async_wait_all();
+            if (!__syncthreads_or(false)) break;
+            ring_fill(ringBase, prm.profile, prm.profStride, (batch + 1) * kFillBatch, pf, P);
+            pf += kFillBatch;
+            while (pf >= P) pf -= P;
+        }
+        return;
+    }
+
     uint32_t colAddr[R];  // ring byte address of this column's fused-pair row (lane and batch-phase offsets folded in)
     uint32_t Hp[R];       // H of the previous row
     uint32_t F[R];        // F for the next row
@@ -153,13 +175,15 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
     const int pRestart = (m == 0) ? 0 : P - m;
     bool haveWork = false;    // a segment is being computed
     bool useBorder = false;   // MULTI: the current segment continues an item (left border comes from `border`)
-    bool alive = true;        // the group still has something to compute, finalise or start
+    bool alive = (warp * (32 >> logG) + g) < prm.activeGroups;  // the group still has something to compute, finalise or start
     uint2 inBuf = make_uint2(0, NEG2), outBuf = make_uint2(0, 0);
 
     // look-ahead: fetch the descriptor of the item / segment that follows and start copying its columns
     auto fetch_lookahead = [&](bool continuing, int curBlock) {
         int blk = -1, isNew = 0, item = -1;
-        if (continuing) {
+        if (!alive) {
+            item = prm.numItems;  // this group never takes work
+        } else if (continuing) {
             blk = curBlock + 1;
         } else {
             if (m == 0) item = atomicAdd(prm.ticket, 1);
