@@ -26,6 +26,7 @@
 #include "blosum_tables.hpp"
 #include "device_db.cuh"
 #include "kernels_s16.cuh"
+#include "kernels_s16_wide.cuh"
 #include "kernels_s32.cuh"
 #include "topk.cuh"
 
@@ -59,14 +60,16 @@ struct Error {
 // ---------------------------------------------------------------------------------------------------------------
 // length classes of the packed 16-bit kernel: G lanes x R columns, capacity G*R
 // ---------------------------------------------------------------------------------------------------------------
-// G = 1<<logG lanes x R columns per lane; capacity = G*R columns per pair-block. The last entry is the multi-segment
-// long class: subjects longer than 1024 are cut into segments of 1024 columns that one warp aligns back to back.
-struct LengthClass { int logG, R, capacity; bool multi; };
+// G = 1<<logG lanes x R columns per lane; capacity = G*R columns per pair-block. Subjects up to 512 residues run on the
+// two-rows-per-step kernel (G = 8 or 16, kernels_s16.cuh); 513..1024 and the multi-segment class (1024-column segments,
+// any length) on the full-warp one-row-per-step variant (G = 32, kernels_s16_wide.cuh).
+struct LengthClass { int logG, R, capacity; bool wide, multi; };
 static const LengthClass kLengthClasses[] = {
-    {3, 4, 32, false},    {3, 8, 64, false},    {3, 12, 96, false},   {3, 16, 128, false},  {3, 20, 160, false},
-    {3, 24, 192, false},  {3, 28, 224, false},  {3, 32, 256, false},  {4, 20, 320, false},  {4, 24, 384, false},
-    {4, 28, 448, false},  {4, 32, 512, false},  {5, 20, 640, false},  {5, 24, 768, false},  {5, 28, 896, false},
-    {5, 32, 1024, false}, {5, 32, 1024, true},
+    {3, 4, 32, false, false},    {3, 8, 64, false, false},    {3, 12, 96, false, false},   {3, 16, 128, false, false},
+    {3, 20, 160, false, false},  {3, 24, 192, false, false},  {3, 28, 224, false, false},  {4, 16, 256, false, false},
+    {4, 20, 320, false, false},  {4, 24, 384, false, false},  {4, 28, 448, false, false},  {4, 32, 512, false, false},
+    {5, 20, 640, true, false},   {5, 24, 768, true, false},   {5, 28, 896, true, false},   {5, 32, 1024, true, false},
+    {5, 32, 1024, true, true},
 };
 constexpr int kNumLengthClasses = sizeof(kLengthClasses) / sizeof(kLengthClasses[0]);
 constexpr int kS16OverflowThreshold = 25000;  // reference MAX_ACC_SHORT, src/kernels.cuh:5
@@ -194,8 +197,8 @@ struct Shard {
     DevBuf<int2> dBorder;
     DevBuf<unsigned long long> dClassNs;  // per length class: run time of its last launch (written by the kernel)
     unsigned long long* hClassNs = nullptr;
-    DevBuf<uint2> dBorder16;   // left/right border columns of the multi-segment class, one row array per warp
-    size_t border16Stride = 0;
+    DevBuf<uint2> dBorderWide;  // left/right border columns of the multi-segment class, one row array per warp
+    size_t borderWideStride = 0;
     DevBuf<TopkCand> dCand;
     DevBuf<int32_t> dTopScores, dTopIds;
     // pinned host staging
@@ -225,21 +228,47 @@ struct Shard {
     }
 };
 
+// steps (row pairs) between two alignments of a group: ceil(q/2) + G - 1 rounded up to a batch, at least 16 so that
+// no lane of a half-warp starts before step 0
+static inline int s16Period(int qlen, int G) { return std::max(16, ((qlen + 1) / 2 + G - 1 + 7) / 8 * 8); }
+// the wide variant advances one row per step: q + G - 1 rounded up to 8, at least 32
+static inline int s16WidePeriod(int qlen, int G) { return std::max(32, (qlen + G - 1 + 7) / 8 * 8); }
+
+template <class Kernel, class Params>
+static void launch_clustered(Kernel kernel, const Params& prm, int grid, int smemBytes, cudaStream_t stream);
+
 template <int R, bool MULTI>
+static void launch_s16_wide(const S16WideParams& prm, int grid, cudaStream_t stream) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        SW4_CUDA(cudaFuncSetAttribute(sw_s16_wide_kernel<R, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16_wide_smem_bytes<R>()));
+        configured[dev & 63] = true;
+    }
+    launch_clustered(sw_s16_wide_kernel<R, MULTI>, prm, grid, s16_wide_smem_bytes<R>(), stream);
+}
+
+template <int R>
 static void launch_s16(const S16Params& prm, int grid, cudaStream_t stream) {
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        SW4_CUDA(cudaFuncSetAttribute(sw_s16_kernel<R, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16_smem_bytes<R>()));
+        SW4_CUDA(cudaFuncSetAttribute(sw_s16_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16_smem_bytes<R>()));
         configured[dev & 63] = true;
     }
+    launch_clustered(sw_s16_kernel<R>, prm, grid, s16_smem_bytes<R>(), stream);
+}
+
+template <class Kernel, class Params>
+static void launch_clustered(Kernel kernel, const Params& prm, int grid, int smemBytes, cudaStream_t stream) {
     // CTAs are launched as clusters of 2 whenever the grid is even: the two SMs of a TPC share an instruction cache, and
     // with 17 different (large, heavily unrolled) kernels resident at once it pays to give both SMs the same code.
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kS16Threads);
-    cfg.dynamicSmemBytes = s16_smem_bytes<R>();
+    cfg.dynamicSmemBytes = (size_t)smemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -248,7 +277,7 @@ static void launch_s16(const S16Params& prm, int grid, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SW4_CUDA(cudaLaunchKernelEx(&cfg, sw_s16_kernel<R, MULTI>, prm));
+    SW4_CUDA(cudaLaunchKernelEx(&cfg, kernel, prm));
 }
 
 struct Engine {
@@ -481,7 +510,7 @@ struct Engine {
             sh.hTopCap = topWords + 64;
             SW4_CUDA(cudaMallocHost(&sh.hTop, sh.hTopCap * sizeof(int32_t)));
         }
-        const int profStride = (qlen + 31 + 3) / 4 * 4 + 16;
+        const int profStride = (qlen + 64 + 3) / 4 * 4;  // >= 2 * period of any class
         // All device scratch is sized here, BEFORE the timed region, for a query capacity that only grows by doubling:
         // cudaMalloc/cudaFree inside the event-bracketed region stall the stream for up to hundreds of milliseconds.
         if (qlen > sh.queryCapacity || k > sh.topCapacity) {
@@ -490,7 +519,7 @@ struct Engine {
             while (cap < qlen) cap *= 2;
             sh.queryCapacity = cap;
             sh.topCapacity = std::max(sh.topCapacity, std::max(k, 64));
-            const size_t capStride = (size_t)(cap + 31 + 3) / 4 * 4 + 16;
+            const size_t capStride = (size_t)(cap + 64 + 3) / 4 * 4;
             sh.dQueryLetters.ensure((size_t)cap + 16);
             sh.dQueryCodes.ensure((size_t)cap + 16);
             sh.dProfile.ensure((size_t)kFused * capStride);
@@ -504,8 +533,8 @@ struct Engine {
             sh.dBorder.ensure(sh.borderWarps * capBorderStride);
             bool anyMulti = false;
             for (auto& cl : sh.classes) anyMulti |= kLengthClasses[cl->cls].multi;
-            sh.border16Stride = capBorderStride;
-            sh.dBorder16.ensure(anyMulti ? (size_t)sh.smCount * kS16Warps * capBorderStride : 1);
+            sh.borderWideStride = capBorderStride;  // rows
+            sh.dBorderWide.ensure(anyMulti ? (size_t)sh.smCount * kS16Warps * capBorderStride : 1);
         }
         memcpy(sh.hQuery, query, (size_t)qlen);
 
@@ -542,10 +571,10 @@ struct Engine {
                 const LengthClass& lc = kLengthClasses[cl.cls];
                 const int G = 1 << lc.logG;
                 const int groupsPerCta = kS16Warps * (32 >> lc.logG);
-                const int period = std::max(32, (qlen + G - 1 + 7) / 8 * 8);
+                const int period = lc.wide ? s16WidePeriod(qlen, G) : s16Period(qlen, G);
                 // a class may spread out to as few as 4 busy warps per SM (one per scheduler) when there are SMs to spare
                 cap[ci] = std::max(1, (cl.numItems + 3) / 4);
-                cost[ci] = (double)cl.numBlocks / groupsPerCta * period * (lc.R * 7.3 + 30.0) * cl.rate;
+                cost[ci] = (double)cl.numBlocks / groupsPerCta * period * (lc.wide ? lc.R * 7.3 + 30.0 : lc.R * 14.6 + 40.0) * cl.rate;
                 grid[ci] = 1;
                 used++;
             }
@@ -571,45 +600,64 @@ struct Engine {
             SW4_CUDA(cudaStreamWaitEvent(cst, sh.evFork, 0));
             cl.lastCost = cost[ci] / cl.rate;
             cl.lastGrid = grid[ci];
-            S16Params prm{};
-            prm.cols = cl.cols.p;
-            prm.items = cl.items.p;
-            prm.numItems = cl.numItems;
-            prm.ticket = sh.dCounters.p + 8 + cl.cls;
-            prm.logG = lc.logG;
-            prm.profile = sh.dProfile.p;
-            prm.profStride = profStride;
-            prm.qlen = qlen;
-            prm.period = std::max(32, (qlen + G - 1 + 7) / 8 * 8);  // >= 32 so that no lane starts before step 0
-            prm.gop2 = gop2;
-            prm.gex2 = gex2;
-            prm.ovfThreshold = kS16OverflowThreshold;
-            prm.statThreshold = (lc.capacity > 240) ? statThreshold() : 0x7fffffff;
-            prm.scores = sh.dScores.p;
-            prm.ovfList = sh.dOvfList.p;
-            prm.ovfCount = sh.dCounters.p + 0;
-            prm.statCount = sh.dCounters.p + 1;
-            prm.elapsedNs = sh.dClassNs.p + cl.cls;
-            {
-                const int groupsPerCta = kS16Warps * (32 >> lc.logG);
-                prm.activeGroups = std::min(groupsPerCta, std::max(1, (cl.numItems + grid[ci] - 1) / grid[ci]));
+            const int groupsPerCta = kS16Warps * (32 >> lc.logG);
+            const int activeGroups = std::min(groupsPerCta, std::max(1, (cl.numItems + grid[ci] - 1) / grid[ci]));
+            auto fillCommon = [&](auto& prm) {
+                prm.cols = cl.cols.p;
+                prm.items = cl.items.p;
+                prm.numItems = cl.numItems;
+                prm.ticket = sh.dCounters.p + 8 + cl.cls;
+                prm.logG = lc.logG;
+                prm.profile = sh.dProfile.p;
+                prm.profStride = profStride;
+                prm.qlen = qlen;
+                prm.gop2 = gop2;
+                prm.gex2 = gex2;
+                prm.ovfThreshold = kS16OverflowThreshold;
+                prm.statThreshold = (lc.capacity > 240) ? statThreshold() : 0x7fffffff;
+                prm.scores = sh.dScores.p;
+                prm.ovfList = sh.dOvfList.p;
+                prm.ovfCount = sh.dCounters.p + 0;
+                prm.statCount = sh.dCounters.p + 1;
+                prm.elapsedNs = sh.dClassNs.p + cl.cls;
+                prm.activeGroups = activeGroups;
+            };
+            S16Params narrow{};
+            S16WideParams wide{};
+            if (lc.wide) {
+                fillCommon(wide);
+                wide.period = s16WidePeriod(qlen, G);
+                wide.border = sh.dBorderWide.p;
+                wide.borderStride = (int)sh.borderWideStride;
+            } else {
+                fillCommon(narrow);
+                narrow.period = s16Period(qlen, G);
             }
-            prm.border = sh.dBorder16.p;
-            prm.borderStride = (int)sh.border16Stride;
             auto launchClass = [&](int g, cudaStream_t strm, int ctaOffset) {
-                prm.ctaOffset = ctaOffset;
-                if (lc.multi) {
-                    launch_s16<32, true>(prm, g, strm);
+                if (lc.wide) {
+                    wide.ctaOffset = ctaOffset;
+                    if (lc.multi) {
+                        launch_s16_wide<32, true>(wide, g, strm);
+                    } else {
+                        switch (lc.R) {
+                            case 20: launch_s16_wide<20, false>(wide, g, strm); break;
+                            case 24: launch_s16_wide<24, false>(wide, g, strm); break;
+                            case 28: launch_s16_wide<28, false>(wide, g, strm); break;
+                            case 32: launch_s16_wide<32, false>(wide, g, strm); break;
+                            default: fail(SW4_ERR_INVALID, "no wide kernel for R=%d", lc.R);
+                        }
+                    }
                 } else {
+                    narrow.ctaOffset = ctaOffset;
                     switch (lc.R) {
-                        case 4: launch_s16<4, false>(prm, g, strm); break;
-                        case 8: launch_s16<8, false>(prm, g, strm); break;
-                        case 12: launch_s16<12, false>(prm, g, strm); break;
-                        case 16: launch_s16<16, false>(prm, g, strm); break;
-                        case 20: launch_s16<20, false>(prm, g, strm); break;
-                        case 24: launch_s16<24, false>(prm, g, strm); break;
-                        case 28: launch_s16<28, false>(prm, g, strm); break;
-                        case 32: launch_s16<32, false>(prm, g, strm); break;
+                        case 4: launch_s16<4>(narrow, g, strm); break;
+                        case 8: launch_s16<8>(narrow, g, strm); break;
+                        case 12: launch_s16<12>(narrow, g, strm); break;
+                        case 16: launch_s16<16>(narrow, g, strm); break;
+                        case 20: launch_s16<20>(narrow, g, strm); break;
+                        case 24: launch_s16<24>(narrow, g, strm); break;
+                        case 28: launch_s16<28>(narrow, g, strm); break;
+                        case 32: launch_s16<32>(narrow, g, strm); break;
                         default: fail(SW4_ERR_INVALID, "no kernel for R=%d", lc.R);
                     }
                 }

@@ -1,26 +1,35 @@
-// Inter-sequence Gotoh score kernel, packed s16x2 (two subjects per lane), for subjects that fit one register tile.
+// Inter-sequence Gotoh score kernel, packed s16x2 (two subjects per 32-bit lane register), subjects up to 512 residues.
 //
-// Replaces the reference's NW_local_affine_single_pass_dpx_s16 family (src/dpx_s16_kernels.cuh:764-1055, 1220-1357)
-// with a different organisation, designed around what the B200 SM measures (tools/ubench/pipes.cu, profiles/):
-// DPX min/max ops issue on the ALU pipe at 2 warp-inst/clk/SM, VIADD.16x2 on the FMA pipe at 2/clk/SM, issue is
-// 4/clk/SM and shared memory serves one conflict-free 32-lane request per clock. The recurrence needs 3.5 ALU-pipe
-// ops + 2 VIADD + 1 substitution fetch per cell-pair, so everything else must cost ~0:
+// Replaces the reference's NW_local_affine_{single,multi}_pass_dpx_s16 family (src/dpx_s16_kernels.cuh:290-1357)
+// with a different organisation, designed around what the B200 SM measures (tools/ubench/, profiles/ubench_*.txt):
+// DPX min/max ops issue on the ALU pipe at 1 warp-inst / 2 clk / scheduler, VIADD.16x2 on the FMA-heavy pipe, shared
+// memory serves one conflict-free 128-byte request per clock, and every instruction that is not one of the 3.5 DPX ops
+// a cell-pair needs costs close to a full issue slot. So the loop must contain nothing but the recurrence:
 //
-//  * Warp = one 32-stage systolic pipeline (lane l works on query row t-l at step t), cut into 32/G independent
-//    groups of G lanes; each group aligns one *pair-block* (two subjects, G*R columns, R register columns per lane)
-//    and groups restart back-to-back on their own schedule (period P = q+G-1 rounded to 4), so there is no
-//    warp-wide fill/drain.
-//  * Substitution scores come from a *positional* query profile: prof[f][p] = (M[q_p][s1] << 16 | M[q_p][s0]) for the
-//    fused residue pair f = s0 + 21*s1. A 64-step sliding window of it lives in shared memory as ring[f][96]
-//    (64 slots + 32 mirrored), refilled with cp.async 16 steps ahead. Lane l reads slot (t-l): the 32 lanes of a warp
-//    always hit 32 different banks (no conflicts, whatever the residues are), and the address is
-//    (per-column register, fixed for the whole alignment) + (warp-uniform step offset): no per-cell address math.
-//  * The device database stores pair-blocks as the fused u16 column codes (cudasw4_b200/csrc/device_db.cuh), fetched
-//    one block ahead with cp.async into a per-group staging area.
+//  * Half-warp = one 16-stage systolic pipeline. Lane l (0..15 inside its half-warp) works on query rows 2(t-l) and
+//    2(t-l)+1 at step t: TWO rows per step, so a column's two substitution words come from ONE 64-bit shared load,
+//    F[j]/Hp[j] are read and written once per two rows, the two rows' E chains interleave (ILP 2) and the per-step
+//    bookkeeping (hand-over shuffles, counters) is amortised over 2*R cell-pairs. A half-warp is cut into 16/G groups
+//    (G = 8 or 16 lanes); a group aligns one *pair-block* (two subjects, G*R columns, R register columns per lane) and
+//    restarts on its own schedule every P steps (P = ceil(q/2)+G-1 rounded to 8): no warp-wide fill/drain.
+//    Row pairs in [q, 2P) are *gap rows*: computed like any other row (no branch, hence no register shuffling at a merge
+//    point) on profile entries of -16000 with the hand-over inputs forced to the boundary values.
+//  * Substitution scores come from a *positional* query profile prof[f][row] = (M[q_row][s1] << 16 | M[q_row][s0]) for
+//    the fused residue pair f = s0 + 21*s1. A 64-row sliding window lives in shared memory as ring[f][96] (64 slots +
+//    32 mirrored), refilled 16 rows ahead with cp.async. Lane l reads rows 2(t-l), 2(t-l)+1: the 16 lanes of a
+//    half-warp (one LDS.64 wavefront) always cover 32 different banks - no conflicts whatever the residues are - and
+//    the address is (per-column register, fixed for the whole alignment) + (instruction immediate): the 8 steps of a
+//    batch are unrolled and the column addresses advance by 64 bytes once per batch. No per-cell address arithmetic.
+//  * The device database stores pair-blocks as fused u16 column codes (device_db.cuh), fetched one alignment ahead with
+//    cp.async into a per-group staging area; work items are handed out through an atomic ticket.
+//  * Subjects longer than 512 run on the full-warp, one-row-per-step variant (kernels_s16_wide.cuh): a 32-lane group
+//    at two rows per lane would need a 128-row ring, which does not fit next to the staging area.
 //
 // Arithmetic (bit-exact vs the oracle): H = max(0, diag+s, E, F); t = H+gop; E' = max(E+gex, t); F' = max(F+gex, t);
-// packed modular s16 adds, -16000 as minus infinity; a pair whose running maximum reaches `ovfThreshold` is
-// re-scored in 32 bit (kernels_s32.cuh), exactly the reference's envelope argument.
+// packed modular s16 adds, -16000 as minus infinity; the running maximum is taken over diag+s (equal to max H: a best
+// local alignment ends on a match; and the second use keeps ptxas from fusing the add into an ALU-pipe VIADDMNMX).
+// A pair whose maximum reaches `ovfThreshold` is re-scored in 32 bit (kernels_s32.cuh): the reference's envelope
+// argument.
 #pragma once
 #include <cstdint>
 #include <utility>
@@ -30,15 +39,16 @@ namespace sw4 {
 
 constexpr int kS16Threads = 512;           // 16 warps, one CTA per SM
 constexpr int kS16Warps = kS16Threads / 32;
-constexpr int kRingSlots = 64;
+constexpr int kRingSlots = 64;             // query rows held in the ring
 constexpr int kRingStride = 96;            // words per fused-pair row: 32 mirrored + 64 live slots
 constexpr int kFused = 441;                // 21 x 21 residue pairs
-constexpr int kFillBatch = 16;             // steps between ring refills / CTA barriers
+constexpr int kBatchSteps = 8;             // steps between ring refills / CTA barriers (unrolled)
+constexpr int kBatchRows = 2 * kBatchSteps;
 constexpr int kRingBytes = kFused * kRingStride * 4;
 constexpr short kNegS16 = -16000;
 
 // One unit of work for a group: a pair of subjects occupying `numSegments` consecutive pair-blocks (1 for every
-// subject that fits the class's G*R columns; > 1 only in the multi-segment long class, where segment s holds columns
+// subject that fits the class's G*R columns; > 1 only in the multi-segment class, where segment s holds columns
 // [s*G*R, (s+1)*G*R) and the last column's (H, E) of every query row is handed to the next segment through `border`).
 struct S16Item {
     int subject0, subject1;   // local subject index of the low / high half (-1 = none)
@@ -51,11 +61,11 @@ struct S16Params {
     const S16Item* items;        // [numItems] in the order they should be started
     int numItems;
     int* ticket;                 // zero-initialised work counter (items are handed out dynamically)
-    int logG;                    // G = 1 << logG lanes per group
-    const uint32_t* profile;     // [441][profStride] positional query profile
+    int logG;                    // G = 1 << logG lanes per group, 8 or 16
+    const uint32_t* profile;     // [441][profStride] positional query profile, rows >= qlen hold -16000
     int profStride;
     int qlen;
-    int period;                  // P: steps between two alignments of a group; multiple of 8, >= max(32, qlen + G - 1); G >= 8
+    int period;                  // P: steps between two alignments of a group; multiple of 8, >= max(16, ceil(q/2) + G - 1)
     uint32_t gop2, gex2;         // gap scores replicated in both halves
     int ovfThreshold;            // running maximum >= this => exact 32-bit re-scoring (25000, reference MAX_ACC_SHORT)
     int statThreshold;           // running maximum >= this => counted in stats.num_overflows (25000, or 2048 for Half2)
@@ -67,8 +77,6 @@ struct S16Params {
     int activeGroups;            // groups per CTA that take work (fewer than all when the class cannot fill its SMs: the
                                  // items are then spread over more SMs and every warp gets a larger share of its scheduler)
     int ctaOffset;               // index of this launch's first CTA within the class (a class may be split in two launches)
-    uint2* border;               // MULTI only: [gridWarps][borderStride] (H, E) of a segment's last column per query row
-    int borderStride;
 };
 
 template <int N, class Fn, int... Is>
@@ -87,6 +95,12 @@ __device__ __forceinline__ uint32_t lds_u32_imm(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
     return v;
 }
+template <int IMM>
+__device__ __forceinline__ uint2 lds_u64_imm(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(addr), "n"(IMM));
+    return v;
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
 }
@@ -99,19 +113,16 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 constexpr int kGroupStateInts = 8;  // per-group bookkeeping kept in shared memory (touched at restarts only)
 
 template <int R>
-constexpr int s16_smem_bytes() { return kRingBytes + kS16Warps * 32 * R * 2 + kS16Warps * 8 * kGroupStateInts * 4; }
+constexpr int s16_smem_bytes() { return kRingBytes + kS16Warps * 32 * R * 2 + kS16Warps * 4 * kGroupStateInts * 4; }
 
-// Refill ring slots for global steps [x0, x0+16) (x0 % 16 == 0); p0 = x0 mod period.
+// Refill the ring slots of query rows [x0, x0+16) (x0 % 16 == 0); p0 = x0 mod periodRows (periodRows % 16 == 0).
 __device__ __forceinline__ void ring_fill(uint32_t ringBase, const uint32_t* __restrict__ profile, int profStride, int x0,
-                                          int p0, int period) {
+                                          int p0) {
     const int slot0 = x0 & (kRingSlots - 1);
-    for (int id = threadIdx.x; id < kFused * (kFillBatch / 4); id += kS16Threads) {
+    for (int id = threadIdx.x; id < kFused * (kBatchRows / 4); id += kS16Threads) {
         const int f = id >> 2, c = id & 3;
-        int p = p0 + 4 * c;
-        if (p >= period) p -= period;
-        if (p >= period) p -= period;
         const int slot = slot0 + 4 * c;
-        const uint32_t* src = profile + (size_t)f * profStride + p;
+        const uint32_t* src = profile + (size_t)f * profStride + p0 + 4 * c;
         const uint32_t dst = ringBase + (f * kRingStride + 32 + slot) * 4;
         cp_async16(dst, src);
         if (slot >= 32) cp_async16(dst - kRingSlots * 4, src);
@@ -119,8 +130,8 @@ __device__ __forceinline__ void ring_fill(uint32_t ringBase, const uint32_t* __r
     cp_async_commit();
 }
 
-// R = register columns per lane. MULTI = the long class: G must be 32 and an item may span several segments.
-template <int R, bool MULTI>
+// R = register columns per lane.
+template <int R>
 __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params prm) {
     static_assert(R % 4 == 0, "a lane's staging slice (R u16 codes) must be a whole number of 8-byte chunks");
     extern __shared__ __align__(16) unsigned char smem[];
@@ -128,55 +139,55 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tStart));
     const uint32_t ringBase = (uint32_t)__cvta_generic_to_shared(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int logG = MULTI ? 5 : prm.logG, G = 1 << logG;
-    const int g = lane >> logG, m = lane & (G - 1);
-    const int P = prm.period;
-    const unsigned groupMask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (g << logG));
-    const int leader = g << logG;  // lane index of the group's first lane
+    const int hl = lane & 15;                          // lane inside its half-warp = pipeline stage
+    const int logG = prm.logG, G = 1 << logG;
+    const int g = lane >> logG, m = lane & (G - 1);    // group inside the warp, lane inside the group
+    const int groupsPerWarp = 32 >> logG;
+    const int P = prm.period;                          // steps
+    const int periodRows = 2 * P;
+    const unsigned groupMask = ((G == 16 ? 0xffffu : 0xffu)) << (g << logG);
+    const int leader = g << logG;                      // lane index of the group's first lane
+    const uint32_t NEG2 = ((uint32_t)(uint16_t)kNegS16 << 16) | (uint16_t)kNegS16;
+
+    // Warps that will never get work (the class was spread over more SMs than it can fill, prm.activeGroups) only keep
+    // the CTA's ring going: same barriers and their share of every refill, none of the arithmetic, so the busy warps get
+    // their scheduler to themselves.
+    if (warp * groupsPerWarp >= prm.activeGroups) {
+        for (int i = threadIdx.x; i < kFused * kRingStride; i += kS16Threads) reinterpret_cast<uint32_t*>(smem)[i] = NEG2;
+        __syncthreads();
+        ring_fill(ringBase, prm.profile, prm.profStride, 0, 0);
+        int pf = kBatchRows % periodRows;
+#pragma unroll 1
+        for (int batch = 0;; ++batch) {
+            cp_async_wait_all();
+            if (!__syncthreads_or(false)) break;
+            ring_fill(ringBase, prm.profile, prm.profStride, (batch + 1) * kBatchRows, pf);
+            pf += kBatchRows;
+            if (pf >= periodRows) pf -= periodRows;
+        }
+        return;
+    }
 
     // this lane's slice of the group's staging area: R fused u16 column codes of the next pair-block
     const uint32_t stageLane = ringBase + kRingBytes + (warp * 32 + lane) * (R * 2);
     // group state in shared memory: [0] subject0 [1] subject1 [2] segments left after the current one
     // [3] look-ahead valid [4] look-ahead block [5] look-ahead starts a new item [6] look-ahead item index
     volatile int* gs = reinterpret_cast<volatile int*>(smem + kRingBytes + kS16Warps * 32 * R * 2) +
-                       (warp * 8 + g) * kGroupStateInts;
-    uint2* border = MULTI ? prm.border + (size_t)((blockIdx.x + prm.ctaOffset) * kS16Warps + warp) * prm.borderStride : nullptr;
-
-    // Warps that will never get work (the class was spread over more SMs than it can fill, prm.activeGroups) only keep
-    // the CTA's ring going: same barriers and their share of every refill, none of the arithmetic, so the busy warps get
-    // their scheduler to themselves.
-    if (warp * (32 >> logG) >= prm.activeGroups) {
-        const uint32_t NEG2i = ((uint32_t)(uint16_t)kNegS16 << 16) | (uint16_t)kNegS16;
-        for (int i = threadIdx.x; i < kFused * kRingStride; i += kS16Threads) reinterpret_cast<uint32_t*>(smem)[i] = NEG2i;
-        __syncthreads();
-        ring_fill(ringBase, prm.profile, prm.profStride, 0, 0, P);
-        int pf = kFillBatch % P;
-#pragma unroll 1
-        for (int batch = 0;; ++batch) {
-            cp_async_wait_all();
-            if (!__syncthreads_or(false)) break;
-            ring_fill(ringBase, prm.profile, prm.profStride, (batch + 1) * kFillBatch, pf, P);
-            pf += kFillBatch;
-            while (pf >= P) pf -= P;
-        }
-        return;
-    }
+                       (warp * 4 + g) * kGroupStateInts;
 
     uint32_t colAddr[R];  // ring byte address of this column's fused-pair row (lane and batch-phase offsets folded in)
-    uint32_t Hp[R];       // H of the previous row
-    uint32_t F[R];        // F for the next row
-    const uint32_t NEG2 = ((uint32_t)(uint16_t)kNegS16 << 16) | (uint16_t)kNegS16;
-    uint32_t mx = 0, Elast = NEG2, HinPrev = 0;
+    uint32_t Hp[R];       // H of the lower row (b) of the previous step
+    uint32_t F[R];        // F for the upper row (a) of the next step
+    uint32_t mx = 0, HlastA = 0, ElastA = NEG2, ElastB = NEG2, HinPrevB = 0;
 #pragma unroll
     for (int j = 0; j < R; j++) { colAddr[j] = ringBase; Hp[j] = 0; F[j] = NEG2; }
-    // p = this lane's row in the period-P schedule, (t - lane) mod P. The group restarts (stores the finished pair,
-    // loads the next one) when its first lane is at row 0, i.e. when this lane is at row pRestart.
-    int p = (lane == 0) ? 0 : P - lane;
+    // p = this lane's step in the period-P schedule, (t - hl) mod P: it works on query rows 2p and 2p+1. The group
+    // restarts (stores the finished pair, loads the next one) when its first lane is at step 0, i.e. when this lane is at
+    // step pRestart. Restarts can only fall on the first step of a batch (P and the group offsets are multiples of 8).
+    int p = (hl == 0) ? 0 : P - hl;
     const int pRestart = (m == 0) ? 0 : P - m;
     bool haveWork = false;    // a segment is being computed
-    bool useBorder = false;   // MULTI: the current segment continues an item (left border comes from `border`)
-    bool alive = (warp * (32 >> logG) + g) < prm.activeGroups;  // the group still has something to compute, finalise or start
-    uint2 inBuf = make_uint2(0, NEG2), outBuf = make_uint2(0, 0);
+    bool alive = (warp * groupsPerWarp + g) < prm.activeGroups;  // the group still has something to compute or start
 
     // look-ahead: fetch the descriptor of the item / segment that follows and start copying its columns
     auto fetch_lookahead = [&](bool continuing, int curBlock) {
@@ -209,137 +220,124 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
     // slots must read as gap rows too, so the whole ring starts out as -16000; then the first batch + first pair-blocks.
     for (int i = threadIdx.x; i < kFused * kRingStride; i += kS16Threads) reinterpret_cast<uint32_t*>(smem)[i] = NEG2;
     __syncthreads();
-    ring_fill(ringBase, prm.profile, prm.profStride, 0, 0, P);
+    ring_fill(ringBase, prm.profile, prm.profStride, 0, 0);
     fetch_lookahead(false, 0);
-    int pfill = kFillBatch % P;  // (next fill start) mod P
+    int pfill = kBatchRows % periodRows;  // (first row of the next fill) mod periodRows
 
-    // The step offset inside the ring is an instruction immediate: 16 steps are unrolled and the column addresses are
-    // advanced by 64 bytes once per batch (ptxas does not fold a uniform register into LDS addresses, and an
-    // address add per cell would cost an issue slot per cell-pair).
-    uint32_t phaseBase = ringBase + (32 - lane) * 4;  // + 64 bytes per batch, wrapping every 4 batches
+    uint32_t phaseBase = ringBase + (32 - 2 * hl) * 4;  // + 64 bytes (16 rows) per batch, wrapping every 4 batches
 #pragma unroll 1
     for (int batch = 0;; ++batch) {
         cp_async_wait_all();
         if (!__syncthreads_or(alive)) break;
-        ring_fill(ringBase, prm.profile, prm.profStride, (batch + 1) * kFillBatch, pfill, P);
-        pfill += kFillBatch;
-        while (pfill >= P) pfill -= P;
+        ring_fill(ringBase, prm.profile, prm.profStride, (batch + 1) * kBatchRows, pfill);
+        pfill += kBatchRows;
+        if (pfill >= periodRows) pfill -= periodRows;
         if (batch > 0) {
-            const int delta = (batch & 3) ? kFillBatch * 4 : -(kRingSlots - kFillBatch) * 4;
+            const int delta = (batch & 3) ? kBatchRows * 4 : -(kRingSlots - kBatchRows) * 4;
             phaseBase += delta;
 #pragma unroll
             for (int j = 0; j < R; j++) colAddr[j] += delta;
         }
-        static_for<kFillBatch>([&](auto stepIndex) {
-            constexpr int i = decltype(stepIndex)::value;
-            if ((i & 7) == 0 && p == pRestart && alive) {  // group restart: uniform in the group, divergent across groups
+        if (p == pRestart && alive) {  // group restart: uniform in the group, divergent across groups
+            __syncwarp(groupMask);
+            int segsLeft = gs[2];
+            if (haveWork && segsLeft == 0) {  // the item is complete: reduce the maxima and store the two scores
+                uint32_t r = mx;
+                for (int o = G >> 1; o > 0; o >>= 1) r = __vmaxs2(r, __shfl_xor_sync(groupMask, r, o));
+                if (m == 0) {
+                    const int s0 = gs[0], s1 = gs[1];
+                    const int lo = (int)(short)(r & 0xffff), hi = (int)(short)(r >> 16);
+                    if (s0 >= 0) {
+                        if (lo >= prm.statThreshold) atomicAdd(prm.statCount, 1);
+                        if (lo >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = s0;
+                        prm.scores[s0] = lo;
+                    }
+                    if (s1 >= 0) {
+                        if (hi >= prm.statThreshold) atomicAdd(prm.statCount, 1);
+                        if (hi >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = s1;
+                        prm.scores[s1] = hi;
+                    }
+                }
+            }
+            const bool laValid = gs[3] != 0;
+            const int laBlk = gs[4];
+            const bool laNew = gs[5] != 0;
+            haveWork = laValid;
+            alive = laValid;
+            if (laValid) {
+                if (laNew) {
+                    const S16Item it = prm.items[gs[6]];
+                    __syncwarp(groupMask);
+                    if (m == 0) { gs[0] = it.subject0; gs[1] = it.subject1; gs[2] = it.numSegments - 1; }
+                    segsLeft = it.numSegments - 1;
+                    mx = 0;
+                } else {  // (items of this kernel have one segment; kept for symmetry with the wide variant)
+                    __syncwarp(groupMask);
+                    if (m == 0) gs[2] = segsLeft - 1;
+                    segsLeft -= 1;
+                }
+                cp_async_wait_all();
                 __syncwarp(groupMask);
-                int segsLeft = gs[2];
-                if (haveWork && segsLeft == 0) {  // the item is complete: reduce the maxima and store the two scores
-                    uint32_t r = mx;
-                    for (int o = G >> 1; o > 0; o >>= 1) r = __vmaxs2(r, __shfl_xor_sync(groupMask, r, o));
-                    if (m == 0) {
-                        const int s0 = gs[0], s1 = gs[1];
-                        const int lo = (int)(short)(r & 0xffff), hi = (int)(short)(r >> 16);
-                        if (s0 >= 0) {
-                            if (lo >= prm.statThreshold) atomicAdd(prm.statCount, 1);
-                            if (lo >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = s0;
-                            prm.scores[s0] = lo;
-                        }
-                        if (s1 >= 0) {
-                            if (hi >= prm.statThreshold) atomicAdd(prm.statCount, 1);
-                            if (hi >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = s1;
-                            prm.scores[s1] = hi;
-                        }
-                    }
-                }
-                const bool laValid = gs[3] != 0;
-                const int laBlk = gs[4];
-                const bool laNew = gs[5] != 0;
-                haveWork = laValid;
-                alive = laValid;
-                if (laValid) {
-                    if (laNew) {
-                        const S16Item it = prm.items[gs[6]];
-                        __syncwarp(groupMask);
-                        if (m == 0) { gs[0] = it.subject0; gs[1] = it.subject1; gs[2] = it.numSegments - 1; }
-                        segsLeft = it.numSegments - 1;
-                        mx = 0;
-                        useBorder = false;
-                    } else {
-                        __syncwarp(groupMask);
-                        if (m == 0) gs[2] = segsLeft - 1;
-                        segsLeft -= 1;
-                        useBorder = true;
-                    }
-                    cp_async_wait_all();
-                    __syncwarp(groupMask);
 #pragma unroll
-                    for (int b = 0; b < R / 2; b++) {
-                        const uint32_t w = lds_u32_imm<0>(stageLane + b * 4);
-                        colAddr[b * 2 + 0] = phaseBase + (w & 0xffffu) * (kRingStride * 4);
-                        colAddr[b * 2 + 1] = phaseBase + (w >> 16) * (kRingStride * 4);
-                    }
-#pragma unroll
-                    for (int j = 0; j < R; j++) { Hp[j] = 0; F[j] = NEG2; }
-                    HinPrev = 0;
-                    __syncwarp(groupMask);
-                    fetch_lookahead(segsLeft > 0, laBlk);
+                for (int b = 0; b < R / 2; b++) {
+                    const uint32_t w = lds_u32_imm<0>(stageLane + b * 4);
+                    colAddr[b * 2 + 0] = phaseBase + (w & 0xffffu) * (kRingStride * 4);
+                    colAddr[b * 2 + 1] = phaseBase + (w >> 16) * (kRingStride * 4);
                 }
+#pragma unroll
+                for (int j = 0; j < R; j++) { Hp[j] = 0; F[j] = NEG2; }
+                HinPrevB = 0;
+                __syncwarp(groupMask);
+                fetch_lookahead(segsLeft > 0, laBlk);
             }
-            // systolic hand-over from the previous lane (row p was computed there one step earlier)
-            uint32_t Hin = __shfl_up_sync(0xffffffffu, Hp[R - 1], 1);
-            uint32_t Ein = __shfl_up_sync(0xffffffffu, Elast, 1);
-            // Rows p >= q are "gap rows" between two alignments of the group: they are computed like any other row (no
-            // branch => no register shuffling at a merge point) on profile entries of -16000, with the hand-over
-            // inputs forced to the boundary values so that nothing leaks into the freshly reset state; they can
-            // never raise the running maximum.
-            const bool realRow = (unsigned)p < (unsigned)prm.qlen;
-            if constexpr (MULTI) {
-                // left border of a continued item: 32 rows at a time, coalesced; lane 0 is at row p
-                const int p0 = __shfl_sync(0xffffffffu, p, 0);
-                if ((p0 & 31) == 0 && p0 < prm.qlen) inBuf = useBorder ? border[p0 + lane] : make_uint2(0, NEG2);
-                const uint32_t bH = __shfl_sync(0xffffffffu, inBuf.x, p0 & 31);
-                const uint32_t bE = __shfl_sync(0xffffffffu, inBuf.y, p0 & 31);
-                if (m == 0) { Hin = bH; Ein = bE; }
-                if (!realRow) { Hin = 0; Ein = NEG2; }
-            } else {
-                if (m == 0 || !realRow) { Hin = 0; Ein = NEG2; }
-            }
+        }
+        static_for<kBatchSteps>([&](auto stepIndex) {
+            constexpr int i = decltype(stepIndex)::value;
+            // systolic hand-over from the previous lane: it worked on this row pair one step earlier
+            uint32_t HinA = __shfl_up_sync(0xffffffffu, HlastA, 1);
+            uint32_t EinA = __shfl_up_sync(0xffffffffu, ElastA, 1);
+            uint32_t HinB = __shfl_up_sync(0xffffffffu, Hp[R - 1], 1);
+            uint32_t EinB = __shfl_up_sync(0xffffffffu, ElastB, 1);
+            const bool realA = (unsigned)(2 * p) < (unsigned)prm.qlen;
+            const bool realB = (unsigned)(2 * p + 1) < (unsigned)prm.qlen;
+            if (m == 0 || !realA) { HinA = 0; EinA = NEG2; }
+            if (m == 0 || !realB) { HinB = 0; EinB = NEG2; }
             {
-                uint32_t E = Ein;
-                uint32_t d = __vadd2(HinPrev, lds_u32_imm<i * 4>(colAddr[0]));
-                uint32_t dPrev = 0;
+                uint32_t E1 = EinA, E2 = EinB;
+                // substitution words are fetched kPrefetch columns ahead of their use (explicit software pipeline: the
+                // shared-memory latency must not depend on how far ptxas happens to hoist the loads)
+                constexpr int kPrefetch = 5;
+                uint2 sq[kPrefetch + 1];
+#pragma unroll
+                for (int c = 0; c <= kPrefetch && c < R; c++) sq[c] = lds_u64_imm<i * 8>(colAddr[c]);
+                uint32_t da = __vadd2(HinPrevB, sq[0].x);  // row a: diagonal = row b of the previous step, previous lane
+                uint32_t db = __vadd2(HinA, sq[0].y);      // row b: diagonal = row a of this step, previous lane
+                uint32_t ha = 0;
 #pragma unroll
                 for (int j = 0; j < R; j++) {
-                    // look-ahead: the next column's diagonal term reads Hp[j] before this column overwrites it
-                    uint32_t dNext = 0;
-                    if (j + 1 < R) dNext = __vadd2(Hp[j], lds_u32_imm<i * 4>(colAddr[j + 1]));
-                    const uint32_t h = __vimax3_s16x2_relu(d, E, F[j]);
-                    Hp[j] = h;
-                    const uint32_t tt = __vadd2(h, prm.gop2);
-                    E = __viaddmax_s16x2(E, prm.gex2, tt);
-                    F[j] = __viaddmax_s16x2(F[j], prm.gex2, tt);
-                    // max over d == max over H: a best local alignment ends on a match, and d having a second use
-                    // keeps ptxas from fusing the add into an ALU-pipe VIADDMNMX
-                    if (j & 1) mx = __vimax3_s16x2(mx, d, dPrev);
-                    dPrev = d;
-                    d = dNext;
+                    // look-ahead: the next column's diagonal terms are formed before Hp[j] is overwritten
+                    const uint2 sn = sq[(j + 1) % (kPrefetch + 1)];
+                    if (j + 1 + kPrefetch < R) sq[j % (kPrefetch + 1)] = lds_u64_imm<i * 8>(colAddr[j + 1 + kPrefetch]);
+                    uint32_t na = 0, nb = 0;
+                    if (j + 1 < R) na = __vadd2(Hp[j], sn.x);
+                    ha = __vimax3_s16x2_relu(da, E1, F[j]);
+                    const uint32_t ta = __vadd2(ha, prm.gop2);
+                    E1 = __viaddmax_s16x2(E1, prm.gex2, ta);
+                    const uint32_t Fa = __viaddmax_s16x2(F[j], prm.gex2, ta);
+                    if (j + 1 < R) nb = __vadd2(ha, sn.y);
+                    const uint32_t hb = __vimax3_s16x2_relu(db, E2, Fa);
+                    Hp[j] = hb;
+                    const uint32_t tb = __vadd2(hb, prm.gop2);
+                    E2 = __viaddmax_s16x2(E2, prm.gex2, tb);
+                    F[j] = __viaddmax_s16x2(Fa, prm.gex2, tb);
+                    mx = __vimax3_s16x2(mx, da, db);
+                    da = na;
+                    db = nb;
                 }
-                Elast = E;
-                HinPrev = Hin;
-            }
-            if constexpr (MULTI) {
-                // right border: lane 31 has just finished its row p31; collect 32 rows, then store them coalesced
-                const int p31 = __shfl_sync(0xffffffffu, p, 31);
-                const uint32_t vH = __shfl_sync(0xffffffffu, Hp[R - 1], 31);
-                const uint32_t vE = __shfl_sync(0xffffffffu, Elast, 31);
-                if (p31 < prm.qlen && haveWork) {
-                    if (lane == (p31 & 31)) outBuf = make_uint2(vH, vE);
-                    if ((p31 & 31) == 31 || p31 == prm.qlen - 1) {
-                        if (lane <= (p31 & 31)) border[(p31 & ~31) + lane] = outBuf;
-                    }
-                }
+                HlastA = ha;
+                ElastA = E1;
+                ElastB = E2;
+                HinPrevB = HinB;
             }
             if (++p == P) p = 0;
         });
