@@ -702,7 +702,7 @@ struct Engine {
         // top-k
         const long long n = (long long)sh.n;
         if (k > 0 && n > 0) {
-            int blocks = (int)std::min<long long>(std::min<long long>(2LL * sh.smCount, kTopkMaxCandidates / k), (n + 4095) / 4096);
+            int blocks = (int)std::min<long long>(std::min<long long>(sh.smCount, kTopkMaxCandidates / k), (n + 4095) / 4096);
             blocks = std::max(blocks, 1);
             topk_pass1_kernel<<<blocks, kTopkThreads, 0, st>>>(sh.dScores.p, nullptr, n, k, sh.dCand.p);
             const int numCand = blocks * k;

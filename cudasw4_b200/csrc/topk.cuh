@@ -23,6 +23,51 @@ struct TopkCand { int32_t score; int32_t index; };
 
 __device__ __forceinline__ int topk_hi(int s) { return min(max(s, 0) >> 8, kTopkHiBins - 1); }
 
+
+// Block-wide: given hist[0..nbins) in shared memory, find the highest bin b such that (count of entries in bins > b) < k
+// <= (count in bins >= b), or b = 0 when even all bins together hold fewer than k. Returns (b, count above b) in
+// sBin/sAbove. Every thread owns nbins/blockDim consecutive bins; the suffix sums come from a reverse block scan.
+__device__ __forceinline__ void topk_find_bin(const int* hist, int nbins, int k, int baseAbove, int* warpTotals, int* sBin,
+                                              int* sAbove) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nthreads = blockDim.x;
+    const int per = (nbins + nthreads - 1) / nthreads;
+    // thread t owns bins [lo, hi) counted from the TOP: logical index i <-> bin nbins-1-i
+    const int lo = tid * per, hi = min(nbins, lo + per);
+    int mine = 0;
+    for (int i = lo; i < hi; i++) mine += hist[nbins - 1 - i];
+    // inclusive prefix over threads (in top-down order)
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warpTotals[w] = incl;
+    if (tid == 0) { *sBin = 0; *sAbove = -1; }
+    __syncthreads();
+    int before = baseAbove;
+    for (int x = 0; x < w; x++) before += warpTotals[x];
+    const int exclusive = before + incl - mine;  // entries in bins above this thread's range
+    if (exclusive < k && exclusive + mine >= k) {   // the crossing is inside this thread's bins (exactly one thread)
+        int above = exclusive;
+        for (int i = lo; i < hi; i++) {
+            const int c = hist[nbins - 1 - i];
+            if (above + c >= k) { *sBin = nbins - 1 - i; *sAbove = above; break; }
+            above += c;
+        }
+    }
+    __syncthreads();
+    if (*sAbove < 0) {  // fewer than k entries in total: bin 0 decides, everything above it is kept
+        if (tid == 0) {
+            int total = baseAbove;
+            for (int x = 0; x < (nthreads + 31) / 32; x++) total += warpTotals[x];
+            *sAbove = total - hist[0];
+            *sBin = 0;
+        }
+        __syncthreads();
+    }
+}
+
 // scores[begin+i]; indexOf = begin+i (or indices[begin+i] when indices != nullptr, which must be ascending)
 __global__ void __launch_bounds__(kTopkThreads) topk_pass1_kernel(const int32_t* __restrict__ scores,
                                                                   const int32_t* __restrict__ indices, long long n,
@@ -44,15 +89,7 @@ __global__ void __launch_bounds__(kTopkThreads) topk_pass1_kernel(const int32_t*
     __syncthreads();
     for (long long i = begin + tid; i < end; i += blockDim.x) atomicAdd(&hist[topk_hi(scores[i])], 1);
     __syncthreads();
-    if (tid == 0) {
-        int above = 0, b = kTopkHiBins - 1;
-        for (; b > 0; b--) {
-            if (above + hist[b] >= k) break;
-            above += hist[b];
-        }
-        sBin = b; sAbove = above;  // entries in bins > b: `above` (< k); bin b decides (or everything fits: b == 0)
-    }
-    __syncthreads();
+    topk_find_bin(hist, kTopkHiBins, k, 0, warpTotals, &sBin, &sAbove);  // bin b decides (or everything fits: b == 0)
     const int bin = sBin;
     const int aboveBin = sAbove;
     // ---- level 2: exact threshold inside the deciding bin ----
@@ -67,14 +104,8 @@ __global__ void __launch_bounds__(kTopkThreads) topk_pass1_kernel(const int32_t*
         if (topk_hi(s) == bin) atomicAdd(&hist[clippedBin ? 0 : (max(s, 0) & 255)], 1);
     }
     __syncthreads();
-    if (tid == 0) {
-        int above = aboveBin, b = 255;
-        for (; b > 0; b--) {
-            if (above + hist[b] >= k) break;
-            above += hist[b];
-        }
-        sBin = b; sAbove = above; sRunning = 0; sEmitted = 0;
-    }
+    topk_find_bin(hist, 256, k, aboveBin, warpTotals, &sBin, &sAbove);
+    if (tid == 0) { sRunning = 0; sEmitted = 0; }
     __syncthreads();
     const int T = clippedBin ? (bin << 8) : ((bin << 8) | sBin);  // k-th largest score of this range (or lower bound)
     const int need = k - sAbove;                                  // how many entries == T (>= T if clipped) to keep
