@@ -105,6 +105,31 @@ def test_mixed_lengths_all_scores_match_oracle(oracle, blosum, gop, gex):
             assert res.scores == s.tolist() and res.referenceIds == i.tolist()
 
 
+@pytest.mark.parametrize("lo,hi", [(1, 32), (33, 64), (65, 128), (129, 192), (193, 256), (257, 384), (385, 512),
+                                   (513, 768), (769, 1024), (1025, 1700)])
+def test_every_length_class_alone(oracle, lo, hi):
+    """One database per length-class range (so that single classes get the whole GPU and every (G, R) kernel
+    instantiation runs with many rounds), several query lengths incl. odd ones and ones shorter than a pipeline."""
+    rng = np.random.default_rng(1000 + lo)
+    seqs = [synth.random_residues(rng, int(x)) for x in rng.integers(lo, hi + 1, 700)]
+    db = dbformat.from_sequences(seqs)
+    with _engine(numTop=8, blosumType=62) as eng:
+        eng.setDatabase(db)
+        for ql, (blosum, gop, gex) in zip((5, 40, 145, 333), ((62, -11, -1), (45, -13, -2), (80, -10, -1), (50, -13, -2))):
+            q = synth.random_residues(rng, ql)
+            eng.setBlosum(blosum)
+            eng.setGapScores(gop, gex)
+            res = eng.scan(dbformat.decode(q))
+            scores, ids = eng.lastScanAllScores()
+            got = np.empty(db.num_sequences, np.int32)
+            got[ids] = scores
+            ref = oracle.scan(blosum, q, db, gop, gex)
+            bad = np.nonzero(got != ref)[0]
+            assert len(bad) == 0, (ql, blosum, bad[:8], got[bad[:8]], ref[bad[:8]], db.lengths[bad[:8]])
+            s, i = oracle.topk(ref, 8)
+            assert res.scores == s.tolist() and res.referenceIds == i.tolist()
+
+
 def test_planted_homologs_and_ties(oracle):
     recs, queries = synth.config_c1(seed=1, n=1200)
     seqs = [dbformat.encode(s) for _, s in recs]
