@@ -230,6 +230,14 @@ struct Shard {
 
 // steps (row pairs) between two alignments of a group: ceil(q/2) + G - 1 rounded up to a batch, at least 16 so that
 // no lane of a half-warp starts before step 0
+// The 256-column class can run as 16 lanes x 16 columns or as 8 lanes x 32 columns on the same pair-blocks (a block is
+// 256 consecutive column codes either way). 8 x 32 has 8 fewer fill steps per alignment, 16 x 16 the better steady state
+// (fewer live registers): short queries take the former (measured cross-over between q = 600 and 700).
+static inline LengthClass shapeForQuery(const LengthClass& lc, int qlen) {
+    if (lc.capacity == 256 && !lc.wide && qlen < 640) return LengthClass{3, 32, 256, false, false};
+    return lc;
+}
+
 static inline int s16Period(int qlen, int G) { return std::max(16, ((qlen + 1) / 2 + G - 1 + 7) / 8 * 8); }
 // the wide variant advances one row per step: q + G - 1 rounded up to 8, at least 32
 static inline int s16WidePeriod(int qlen, int G) { return std::max(32, (qlen + G - 1 + 7) / 8 * 8); }
@@ -568,7 +576,7 @@ struct Engine {
             int used = 0;
             for (int ci = 0; ci < numClasses; ci++) {
                 const ClassLayout& cl = *sh.classes[ci];
-                const LengthClass& lc = kLengthClasses[cl.cls];
+                const LengthClass lc = shapeForQuery(kLengthClasses[cl.cls], qlen);
                 const int G = 1 << lc.logG;
                 const int groupsPerCta = kS16Warps * (32 >> lc.logG);
                 const int period = lc.wide ? s16WidePeriod(qlen, G) : s16Period(qlen, G);
@@ -594,7 +602,7 @@ struct Engine {
         }
         for (int ci = numClasses - 1; ci >= 0 && qlen > 0; ci--) {
             ClassLayout& cl = *sh.classes[ci];
-            const LengthClass& lc = kLengthClasses[cl.cls];
+            const LengthClass lc = shapeForQuery(kLengthClasses[cl.cls], qlen);
             const int G = 1 << lc.logG;
             cudaStream_t cst = sh.classStreams[ci % kMaxClassStreams];
             SW4_CUDA(cudaStreamWaitEvent(cst, sh.evFork, 0));

@@ -304,9 +304,10 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
             if (m == 0 || !realB) { HinB = 0; EinB = NEG2; }
             {
                 uint32_t E1 = EinA, E2 = EinB;
-                // substitution words are fetched kPrefetch columns ahead of their use (explicit software pipeline: the
-                // shared-memory latency must not depend on how far ptxas happens to hoist the loads)
-                constexpr int kPrefetch = 5;
+                // substitution words are fetched kPrefetch columns ahead of their use: an explicit software pipeline, because
+                // how far ptxas hoists the loads on its own varies with unrelated source changes (measured on the 1M x 256
+                // benchmark: distance 1..4: 6.47, 5: 6.69, 8..16: 6.85 TCUPS for R = 32; 6.82 -> 6.89 for R = 16)
+                constexpr int kPrefetch = 10;
                 uint2 sq[kPrefetch + 1];
 #pragma unroll
                 for (int c = 0; c <= kPrefetch && c < R; c++) sq[c] = lds_u64_imm<i * 8>(colAddr[c]);
