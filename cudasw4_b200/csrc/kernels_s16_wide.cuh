@@ -247,13 +247,21 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_wide_kernel(const S16Wi
             }
             {
                 uint32_t E = Ein;
-                uint32_t d = __vadd2(HinPrev, lds_u32_imm<i * 4>(colAddr[0]));
+                // substitution words are fetched kPrefetch columns ahead of their use (explicit software pipeline, see
+                // kernels_s16.cuh)
+                constexpr int kPrefetch = 8;
+                uint32_t sq[kPrefetch + 1];
+#pragma unroll
+                for (int c = 0; c <= kPrefetch && c < R; c++) sq[c] = lds_u32_imm<i * 4>(colAddr[c]);
+                uint32_t d = __vadd2(HinPrev, sq[0]);
                 uint32_t dPrev = 0;
 #pragma unroll
                 for (int j = 0; j < R; j++) {
                     // look-ahead: the next column's diagonal term reads Hp[j] before this column overwrites it
+                    const uint32_t sn = sq[(j + 1) % (kPrefetch + 1)];
+                    if (j + 1 + kPrefetch < R) sq[j % (kPrefetch + 1)] = lds_u32_imm<i * 4>(colAddr[j + 1 + kPrefetch]);
                     uint32_t dNext = 0;
-                    if (j + 1 < R) dNext = __vadd2(Hp[j], lds_u32_imm<i * 4>(colAddr[j + 1]));
+                    if (j + 1 < R) dNext = __vadd2(Hp[j], sn);
                     const uint32_t h = __vimax3_s16x2_relu(d, E, F[j]);
                     Hp[j] = h;
                     const uint32_t tt = __vadd2(h, prm.gop2);
