@@ -491,7 +491,7 @@ struct Engine {
             std::string warm;
             for (int i = 0; i < 320; i++) warm.push_back("ARNDCQEGHILKMFPSTWYV"[(i * 7) % 20]);
             for (int rep = 0; rep < 2; rep++) {  // twice: the second pass runs with a measured SM partition
-                for (auto& sh : shards) enqueueScan(*sh, warm.data(), (int)warm.size(), std::min(k, kTopkMaxCandidates / 2));
+                enqueueAll(warm.data(), (int)warm.size(), std::min(k, kTopkMaxCandidates / 2));
                 for (auto& sh : shards) { SW4_CUDA(cudaSetDevice(sh->device)); SW4_CUDA(cudaStreamSynchronize(sh->stream)); updateClassRates(*sh); }
             }
             for (auto& sh : shards) { SW4_CUDA(cudaSetDevice(sh->device)); SW4_CUDA(cudaStreamSynchronize(sh->stream)); updateClassRates(*sh); }
@@ -733,6 +733,25 @@ struct Engine {
         SW4_CUDA(cudaEventRecord(sh.evStop, st));
     }
 
+    // One host thread per GPU issues that GPU's launches (the reference drives all GPUs from a single thread in lock-step
+    // phases, src/cudasw4.cuh:1509-2259: ~35 launches x 8 GPUs back to back before the last GPU starts).
+    void enqueueAll(const char* query, int qlen, int k) {
+        if (shards.size() == 1) { enqueueScan(*shards[0], query, qlen, k); return; }
+        std::vector<std::thread> workers;
+        std::vector<Error> errors(shards.size(), Error{SW4_OK, ""});
+        for (size_t i = 1; i < shards.size(); i++)
+            workers.emplace_back([&, i] {
+                try { enqueueScan(*shards[i], query, qlen, k); }
+                catch (const Error& e) { errors[i] = e; }
+                catch (const std::exception& e) { errors[i] = Error{SW4_ERR_INVALID, e.what()}; }
+            });
+        try { enqueueScan(*shards[0], query, qlen, k); }
+        catch (const Error& e) { errors[0] = e; }
+        for (auto& w : workers) w.join();
+        for (auto& e : errors)
+            if (e.code != SW4_OK) throw e;
+    }
+
     // feedback for the SM partition: how many SM-milliseconds a unit of modelled cost really took in the last scan
     static void updateClassRates(Shard& sh) {
         double norm = 0;
@@ -766,7 +785,7 @@ struct Engine {
         // Result lists longer than the device selection keeps (4096) are rare (the reference's CLI default is 10): they take
         // the slow but exact route of copying all scores to the host (the reference's CUDASW_DEBUG_CHECK_CORRECTNESS mode).
         const bool hostSelect = k > kTopkMaxCandidates / 2;
-        for (auto& sh : shards) enqueueScan(*sh, query, qlen, hostSelect ? 0 : k);
+        enqueueAll(query, qlen, hostSelect ? 0 : k);
         double seconds = 0, kernelSeconds = 0;
         int overflows = 0, launches = 0;
         struct Entry { int32_t score, id; };
