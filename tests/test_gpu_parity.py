@@ -146,6 +146,26 @@ def test_planted_homologs_and_ties(oracle):
             assert "hom_q%d_" % qi in eng.getReferenceHeader(res.referenceIds[0])
 
 
+def test_long_query_against_short_subjects(oracle):
+    """Query much longer than the subjects (long periods, many ring refills per alignment), odd and even lengths."""
+    rng = np.random.default_rng(77)
+    seqs = [synth.random_residues(rng, int(n)) for n in rng.integers(20, 520, 600)]
+    db = dbformat.from_sequences(seqs)
+    with _engine(numTop=10, blosumType=62) as eng:
+        eng.setDatabase(db)
+        for ql in (9001, 12000):
+            q = synth.random_residues(rng, ql)
+            q[100:100 + len(seqs[5])] = seqs[5]  # plant one subject inside the query
+            res = eng.scan(dbformat.decode(q))
+            scores, ids = eng.lastScanAllScores()
+            got = np.empty(db.num_sequences, np.int32)
+            got[ids] = scores
+            ref = oracle.scan(62, q, db, -11, -1)
+            assert (got == ref).all(), np.nonzero(got != ref)[0][:10]
+            s, i = oracle.topk(ref, 10)
+            assert res.scores == s.tolist() and res.referenceIds == i.tolist()
+
+
 def test_scores_beyond_16_bit_are_exact(oracle):
     rng = np.random.default_rng(9)
     q = synth.random_residues(rng, 7000)
