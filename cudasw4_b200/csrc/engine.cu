@@ -296,6 +296,9 @@ struct Engine {
     int kernelTypes[4] = {SW4_KERNEL_DPX_S16, SW4_KERNEL_DPX_S16, SW4_KERNEL_DPX_S32, SW4_KERNEL_DPX_S32};
     sw4_mem_config mem{};
     bool verbose = false;
+    // scheduling of the length classes (development switches: SW4_SCHED=partition|backfill, SW4_BACKFILL_ITEMS=n)
+    bool backfill = [] { const char* e = getenv("SW4_SCHED"); return !(e && std::string(e) == "partition"); }();
+    int backfillItems = [] { const char* e = getenv("SW4_BACKFILL_ITEMS"); return e ? std::max(1, atoi(e)) : 4; }();
     int shardRank = 0, shardWorld = 1;
     std::unique_ptr<HostDB> db;
     std::vector<std::unique_ptr<Shard>> shards;
@@ -414,8 +417,8 @@ struct Engine {
         sh.dScores.alloc(n);
         sh.dOvfList.alloc(n);
         sh.dCounters.alloc(kNumCounters);
-        sh.dClassNs.alloc(32);
-        if (!sh.hClassNs) SW4_CUDA(cudaMallocHost(&sh.hClassNs, 32 * sizeof(unsigned long long)));
+        sh.dClassNs.alloc(96);
+        if (!sh.hClassNs) SW4_CUDA(cudaMallocHost(&sh.hClassNs, 96 * sizeof(unsigned long long)));
         sh.dMatrix.alloc(441);
         SW4_CUDA(cudaMemcpyAsync(sh.dChars.p, hChars, totalChars, cudaMemcpyHostToDevice, sh.stream));
         SW4_CUDA(cudaMemcpyAsync(sh.dOffsets.p, offsets.data(), (n + 1) * sizeof(size_t), cudaMemcpyHostToDevice, sh.stream));
@@ -551,7 +554,7 @@ struct Engine {
         SW4_CUDA(cudaMemcpyAsync(sh.dQueryLetters.p, sh.hQuery, (size_t)qlen, cudaMemcpyHostToDevice, st));
         SW4_CUDA(cudaMemcpyAsync(sh.dMatrix.p, matrix, 441, cudaMemcpyHostToDevice, st));
         SW4_CUDA(cudaMemsetAsync(sh.dCounters.p, 0, kNumCounters * sizeof(int), st));
-        SW4_CUDA(cudaMemsetAsync(sh.dClassNs.p, 0, 32 * sizeof(unsigned long long), st));
+        SW4_CUDA(cudaMemsetAsync(sh.dClassNs.p, 0, 96 * sizeof(unsigned long long), st));
         // every scan starts from "-1 = not scored" so that a subject the kernels missed can never keep an old score;
         // empty subjects (and everything, for an empty query) score 0 by definition
         SW4_CUDA(cudaMemsetAsync(sh.dScores.p, qlen == 0 ? 0 : 0xff, std::max<size_t>(sh.n, 1) * sizeof(int32_t), st));
@@ -585,6 +588,22 @@ struct Engine {
                 cost[ci] = (double)cl.numBlocks / groupsPerCta * period * (lc.wide ? lc.R * 7.3 + 30.0 : lc.R * 14.6 + 40.0) * cl.rate;
                 grid[ci] = 1;
                 used++;
+            }
+            if (backfill) {
+                // Back-fill scheduling: every class is launched at (up to) full width, longest subjects first, on its own
+                // stream; one CTA fits per SM, so a later class's CTAs start as earlier CTAs retire and the dynamic
+                // tickets even out the rest. No SM goes idle before the last class runs dry.
+                const int width = sh.smCount >= 2 ? (sh.smCount & ~1) : 1;
+                for (int ci = 0; ci < numClasses; ci++) {
+                    const ClassLayout& cl = *sh.classes[ci];
+                    const LengthClass lc = shapeForQuery(kLengthClasses[cl.cls], qlen);
+                    const int groupsPerCta = kS16Warps * (32 >> lc.logG);
+                    int g = (cl.numItems + groupsPerCta * backfillItems - 1) / (groupsPerCta * backfillItems);
+                    g = std::max(1, std::min(width, g));
+                    if (g > 1) g = (g + 1) & ~1;
+                    grid[ci] = std::min(g, width);
+                }
+                used = sh.smCount;
             }
             while (used < sh.smCount) {  // next SM goes to the class with the largest remaining load per SM
                 int best = -1;
@@ -729,7 +748,7 @@ struct Engine {
             SW4_CUDA(cudaMemcpyAsync(sh.hTop + k, sh.dTopIds.p, (size_t)k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         }
         SW4_CUDA(cudaMemcpyAsync(sh.hTop + 2 * k, sh.dCounters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        SW4_CUDA(cudaMemcpyAsync(sh.hClassNs, sh.dClassNs.p, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        SW4_CUDA(cudaMemcpyAsync(sh.hClassNs, sh.dClassNs.p, 96 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         SW4_CUDA(cudaEventRecord(sh.evStop, st));
     }
 
@@ -756,16 +775,22 @@ struct Engine {
     static void updateClassRates(Shard& sh) {
         double norm = 0;
         int cnt = 0;
+        const bool debug = getenv("SW4_DEBUG_PARTITION") != nullptr;
+        unsigned long long t0 = ~0ull;
+        if (debug && sh.hClassNs)
+            for (auto& clp : sh.classes)
+                if (sh.hClassNs[32 + clp->cls]) t0 = std::min(t0, ~sh.hClassNs[32 + clp->cls]);
         for (auto& clp : sh.classes) {
             ClassLayout& cl = *clp;
             if (cl.lastGrid == 0 || cl.lastCost <= 0 || !sh.hClassNs) continue;
             const double ms = (double)sh.hClassNs[cl.cls] * 1e-6;
             if (ms <= 0) continue;
             const double r = (double)ms * cl.lastGrid / cl.lastCost;
-            if (getenv("SW4_DEBUG_PARTITION"))
-                fprintf(stderr, "[sw4] class %2d (G=%2d R=%2d%s) items %7d blocks %7d grid %3d  %.3f ms  rate %.4g -> %.4g\n", cl.cls,
-                        1 << kLengthClasses[cl.cls].logG, kLengthClasses[cl.cls].R, kLengthClasses[cl.cls].multi ? " multi" : "",
-                        cl.numItems, cl.numBlocks, cl.lastGrid, ms, cl.rate, r);
+            if (debug)
+                fprintf(stderr, "[sw4] class %2d (G=%2d R=%2d%s) items %7d blocks %7d grid %3d  longest CTA %.3f ms  first start %.3f last end %.3f ms  rate %.4g -> %.4g\n",
+                        cl.cls, 1 << kLengthClasses[cl.cls].logG, kLengthClasses[cl.cls].R, kLengthClasses[cl.cls].multi ? " multi" : "",
+                        cl.numItems, cl.numBlocks, cl.lastGrid, ms, (double)(~sh.hClassNs[32 + cl.cls] - t0) * 1e-6,
+                        (double)(sh.hClassNs[64 + cl.cls] - t0) * 1e-6, cl.rate, r);
             cl.rate = (cl.rate == 1.0) ? r : 0.5 * cl.rate + 0.5 * r;
             cl.lastGrid = 0;
             norm += cl.rate;

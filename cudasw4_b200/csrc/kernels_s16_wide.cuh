@@ -295,6 +295,8 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_wide_kernel(const S16Wi
         unsigned long long tEnd;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tEnd));
         atomicMax(prm.elapsedNs, tEnd - tStart);
+        atomicMax(prm.elapsedNs + 32, ~tStart);  // earliest CTA start (as a max of the complement)
+        atomicMax(prm.elapsedNs + 64, tEnd);     // latest CTA end
     }
 }
 

@@ -111,7 +111,8 @@ def config_c2(n: int = 1_000_000, length: int = 256, distinct: bool = False, see
     return dbformat.from_equal_length_matrix(np.ascontiguousarray(codes))
 
 
-def _db_from_sorted_lengths(rng, lengths: np.ndarray, planted: list[np.ndarray] | None = None) -> dbformat.SequenceDB:
+def _db_from_sorted_lengths(rng, lengths: np.ndarray, planted: list[np.ndarray] | None = None,
+                            pool: int | None = None) -> dbformat.SequenceDB:
     """Vectorised builder for big shapes: lengths must be ascending; residues random; `planted` sequences are
     written over the subjects whose length matches best."""
     lengths = np.sort(lengths).astype(np.int64)
@@ -120,11 +121,21 @@ def _db_from_sorted_lengths(rng, lengths: np.ndarray, planted: list[np.ndarray] 
     offsets = np.zeros(n + 1, dtype=np.uint64)
     np.cumsum(padded, out=offsets[1:])
     total = int(offsets[-1])
-    chars = random_residues(rng, total)
-    # padding bytes -> 20
-    pos_in_seq = np.arange(total, dtype=np.int64) - np.repeat(offsets[:-1].astype(np.int64), padded)
-    chars[pos_in_seq >= np.repeat(lengths, padded)] = dbformat.PAD_CODE
-    del pos_in_seq
+    if pool is None:
+        chars = random_residues(rng, total)
+    else:  # very large shapes: tile a random pool at random rotations (subjects are distinct substrings of the pool)
+        chars = np.empty(total, dtype=np.uint8)
+        base = random_residues(rng, pool)
+        for o in range(0, total, pool):
+            m = min(pool, total - o)
+            r = int(rng.integers(0, pool))
+            chars[o:o + m] = np.roll(base, r)[:m]
+    # padding bytes -> 20 (at most 3 per sequence)
+    ends = offsets[:-1].astype(np.int64) + lengths
+    for k in range(3):
+        sel = (padded - lengths) > k
+        chars[ends[sel] + k] = dbformat.PAD_CODE
+    del ends
     if planted:
         used = set()
         for p in planted:
