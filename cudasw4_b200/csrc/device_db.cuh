@@ -36,7 +36,14 @@ __global__ void build_profile_kernel(const uint8_t* __restrict__ qcodes, int qle
     const int f = blockIdx.y;  // fused pair: s0 = f % 21 (low half), s1 = f / 21 (high half)
     if (p >= stride) return;
     uint32_t v = 0xc180c180u;  // (-16000, -16000)
-    if (p < qlen) {
+    if (f >= 441) {
+        // rows 441..461: single-residue plane with the score in the low half, rows 462..482: the same in the high half
+        // (sw_s16_long_kernel adds one entry of each)
+        const int s = (f - 441) % 21;
+        const bool high = f >= 462;
+        const uint32_t m = p < qlen ? (uint32_t)(uint16_t)(int16_t)matrix[qcodes[p] * 21 + s] : 0xc180u;
+        v = high ? (m << 16) : m;
+    } else if (p < qlen) {
         const int qc = qcodes[p];
         const int lo = matrix[qc * 21 + f % 21], hi = matrix[qc * 21 + f / 21];
         v = ((uint32_t)(uint16_t)(int16_t)hi << 16) | (uint16_t)(int16_t)lo;

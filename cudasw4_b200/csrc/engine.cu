@@ -27,6 +27,7 @@
 #include "device_db.cuh"
 #include "kernels_s16.cuh"
 #include "kernels_s16_wide.cuh"
+#include "kernels_s16_long.cuh"
 #include "kernels_s32.cuh"
 #include "topk.cuh"
 
@@ -168,6 +169,7 @@ struct ClassLayout {
 };
 
 constexpr int kMaxClassStreams = 24;
+constexpr int kProfileRows = kFused + 42;  // 441 fused-pair rows + two single-residue planes (kernels_s16_long.cuh)
 
 struct Shard {
     int device = 0;
@@ -195,6 +197,7 @@ struct Shard {
     DevBuf<uint32_t> dProfile;
     DevBuf<int8_t> dMatrix;
     DevBuf<int2> dBorder;
+    DevBuf<uint2> dBorderLong;            // per CTA of the long-subject array kernel: border rows between periods
     DevBuf<unsigned long long> dClassNs;  // per length class: run time of its last launch (written by the kernel)
     unsigned long long* hClassNs = nullptr;
     DevBuf<uint2> dBorderWide;  // left/right border columns of the multi-segment class, one row array per warp
@@ -298,6 +301,7 @@ struct Engine {
     bool verbose = false;
     // scheduling of the length classes (development switches: SW4_SCHED=partition|backfill, SW4_BACKFILL_ITEMS=n)
     bool backfill = [] { const char* e = getenv("SW4_SCHED"); return !(e && std::string(e) == "partition"); }();
+    bool useLongKernel = [] { const char* e = getenv("SW4_NO_LONG_KERNEL"); return !e; }();
     int backfillItems = [] { const char* e = getenv("SW4_BACKFILL_ITEMS"); return e ? std::max(1, atoi(e)) : 4; }();
     int shardRank = 0, shardWorld = 1;
     std::unique_ptr<HostDB> db;
@@ -533,7 +537,7 @@ struct Engine {
             const size_t capStride = (size_t)(cap + 64 + 3) / 4 * 4;
             sh.dQueryLetters.ensure((size_t)cap + 16);
             sh.dQueryCodes.ensure((size_t)cap + 16);
-            sh.dProfile.ensure((size_t)kFused * capStride);
+            sh.dProfile.ensure((size_t)kProfileRows * capStride);
             sh.dTopScores.ensure(sh.topCapacity);
             sh.dTopIds.ensure(sh.topCapacity);
             sh.dCand.ensure((size_t)kTopkMaxCandidates);
@@ -546,6 +550,7 @@ struct Engine {
             for (auto& cl : sh.classes) anyMulti |= kLengthClasses[cl->cls].multi;
             sh.borderWideStride = capBorderStride;  // rows
             sh.dBorderWide.ensure(anyMulti ? (size_t)sh.smCount * kS16Warps * capBorderStride : 1);
+            sh.dBorderLong.ensure(anyMulti ? (size_t)sh.smCount * 8 * capBorderStride : 1);
         }
         memcpy(sh.hQuery, query, (size_t)qlen);
 
@@ -560,7 +565,7 @@ struct Engine {
         SW4_CUDA(cudaMemsetAsync(sh.dScores.p, qlen == 0 ? 0 : 0xff, std::max<size_t>(sh.n, 1) * sizeof(int32_t), st));
         if (qlen > 0 && sh.numZeroLength) SW4_CUDA(cudaMemsetAsync(sh.dScores.p, 0, sh.numZeroLength * sizeof(int32_t), st));
         if (qpad > 0) convert_query_kernel<<<(qpad + 255) / 256, 256, 0, st>>>(sh.dQueryLetters.p, sh.dQueryCodes.p, qlen, qpad);
-        build_profile_kernel<<<dim3((profStride + 127) / 128, kFused), 128, 0, st>>>(sh.dQueryCodes.p, qlen, sh.dMatrix.p,
+        build_profile_kernel<<<dim3((profStride + 127) / 128, kProfileRows), 128, 0, st>>>(sh.dQueryCodes.p, qlen, sh.dMatrix.p,
                                                                                    sh.dProfile.p, profStride);
         SW4_CUDA(cudaGetLastError());
         sh.launches += 2;
@@ -690,6 +695,57 @@ struct Engine {
                 }
                 sh.launches++;
             };
+            // the multi-segment class runs on the CTA-wide array kernel whenever the query is long enough to keep
+            // at least two warps of an array busy (kernels_s16_long.cuh)
+            int longWarps = 0;
+            if (lc.multi && useLongKernel) {
+                const int p0 = (qlen + 32 + 15) / 16 * 16;
+                longWarps = kLongMaxWarps;
+                while (longWarps > 1 && kLongLag * longWarps + 64 > p0) longWarps >>= 1;
+                if (longWarps < 2) longWarps = 0;
+                if (longWarps) {
+                    S16LongParams lp{};
+                    lp.cols = cl.cols.p;
+                    lp.items = cl.items.p;
+                    lp.lengths = sh.dLengths.p;
+                    lp.numItems = cl.numItems;
+                    lp.ticket = sh.dCounters.p + 8 + cl.cls;
+                    lp.warps = longWarps;
+                    lp.ringSlots = s16_long_ring_slots(longWarps);
+                    lp.profLo = sh.dProfile.p + (size_t)kFused * profStride;
+                    lp.profHi = sh.dProfile.p + (size_t)(kFused + 21) * profStride;
+                    lp.profStride = profStride;
+                    lp.qlen = qlen;
+                    lp.period = p0;
+                    lp.gop2 = gop2;
+                    lp.gex2 = gex2;
+                    lp.ovfThreshold = kS16OverflowThreshold;
+                    lp.statThreshold = statThreshold();
+                    lp.scores = sh.dScores.p;
+                    lp.ovfList = sh.dOvfList.p;
+                    lp.ovfCount = sh.dCounters.p + 0;
+                    lp.statCount = sh.dCounters.p + 1;
+                    lp.elapsedNs = sh.dClassNs.p + cl.cls;
+                    lp.border = sh.dBorderLong.p;
+                    lp.borderStride = (int)sh.borderWideStride;
+                    const int smemBytes = s16_long_smem_bytes(longWarps);
+                    static bool configured[64] = {};
+                    if (!configured[sh.device & 63]) {
+                        SW4_CUDA(cudaFuncSetAttribute(sw_s16_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      s16_long_smem_bytes(kLongMaxWarps)));
+                        configured[sh.device & 63] = true;
+                    }
+                    const int ctasPerSm = std::max(1, std::min(kLongMaxWarps / longWarps, (227 * 1024) / (smemBytes + 1024)));
+                    const int g = std::max(1, std::min(cl.numItems, std::min(sh.smCount * ctasPerSm, sh.smCount * 8)));
+                    cl.lastGrid = g;
+                    sw_s16_long_kernel<<<g, longWarps * 32, smemBytes, cst>>>(lp);
+                    SW4_CUDA(cudaGetLastError());
+                    sh.launches++;
+                    SW4_CUDA(cudaEventRecord(sh.evJoin[ci % kMaxClassStreams], cst));
+                    SW4_CUDA(cudaStreamWaitEvent(st, sh.evJoin[ci % kMaxClassStreams], 0));
+                    continue;
+                }
+            }
             // even part as clusters of 2 (same code on both SMs of a TPC), an odd leftover CTA on a second stream;
             // both launches share the class's ticket counter and timing slot
             const int evenPart = grid[ci] & ~1;
