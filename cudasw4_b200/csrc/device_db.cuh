@@ -36,7 +36,10 @@ __global__ void build_profile_kernel(const uint8_t* __restrict__ qcodes, int qle
     const int f = blockIdx.y;  // fused pair: s0 = f % 21 (low half), s1 = f / 21 (high half)
     if (p >= stride) return;
     uint32_t v = 0xc180c180u;  // (-16000, -16000)
-    if (f >= 441) {
+    if (f >= 483) {
+        // rows 483..503: plain int32 plane for the exact 32-bit array kernel (sw_s32_long_kernel)
+        v = p < qlen ? (uint32_t)(int32_t)matrix[qcodes[p] * 21 + (f - 483)] : (uint32_t)(-(1 << 28));
+    } else if (f >= 441) {
         // rows 441..461: single-residue plane with the score in the low half, rows 462..482: the same in the high half
         // (sw_s16_long_kernel adds one entry of each)
         const int s = (f - 441) % 21;

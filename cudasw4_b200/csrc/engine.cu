@@ -29,6 +29,7 @@
 #include "kernels_s16_wide.cuh"
 #include "kernels_s16_long.cuh"
 #include "kernels_s32.cuh"
+#include "kernels_s32_long.cuh"
 #include "topk.cuh"
 
 namespace sw4 {
@@ -169,7 +170,7 @@ struct ClassLayout {
 };
 
 constexpr int kMaxClassStreams = 24;
-constexpr int kProfileRows = kFused + 42;  // 441 fused-pair rows + two single-residue planes (kernels_s16_long.cuh)
+constexpr int kProfileRows = kFused + 63;  // 441 fused-pair rows + two s16 single-residue planes + one int32 plane (array kernels)
 
 struct Shard {
     int device = 0;
@@ -777,8 +778,32 @@ struct Engine {
             SW4_CUDA(cudaGetLastError());
             sh.launches++;
         };
-        if (qlen > 0) {
-            if (!sh.classes.empty()) launchS32(sh.dOvfList.p, sh.dCounters.p + 0, 0, sh.dCounters.p + 3, false);
+        if (qlen > 0 && !sh.classes.empty()) {
+            // long queries (the only ones that can saturate 16 bits) re-score on the CTA-wide array, 16 warps per subject
+            const int p0 = (qlen + 32 + 15) / 16 * 16;
+            if (useLongKernel && kLongLag * kLongMaxWarps + 64 <= p0) {
+                S32LongParams lp{};
+                lp.chars = sh.dChars.p; lp.offsets = sh.dOffsets.p; lp.lengths = sh.dLengths.p;
+                lp.list = sh.dOvfList.p; lp.listCountPtr = sh.dCounters.p + 0; lp.ticket = sh.dCounters.p + 3;
+                lp.warps = kLongMaxWarps;
+                lp.ringSlots = s16_long_ring_slots(kLongMaxWarps);
+                lp.prof = reinterpret_cast<const int32_t*>(sh.dProfile.p + (size_t)(kFused + 42) * profStride);
+                lp.profStride = profStride; lp.qlen = qlen; lp.period = p0; lp.gop = gop; lp.gex = gex;
+                lp.scores = sh.dScores.p;
+                lp.border = reinterpret_cast<int2*>(sh.dBorderLong.p);
+                lp.borderStride = (int)sh.borderWideStride;
+                const int smemBytes = s32_long_smem_bytes(kLongMaxWarps);
+                static bool configured[64] = {};
+                if (!configured[sh.device & 63]) {
+                    SW4_CUDA(cudaFuncSetAttribute(sw_s32_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
+                    configured[sh.device & 63] = true;
+                }
+                sw_s32_long_kernel<<<sh.smCount, kLongMaxWarps * 32, smemBytes, st>>>(lp);
+                SW4_CUDA(cudaGetLastError());
+                sh.launches++;
+            } else {
+                launchS32(sh.dOvfList.p, sh.dCounters.p + 0, 0, sh.dCounters.p + 3, false);
+            }
         }
         SW4_CUDA(cudaEventRecord(sh.evK1, st));
 
