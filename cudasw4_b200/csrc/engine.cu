@@ -67,11 +67,14 @@ struct Error {
 // any length) on the full-warp one-row-per-step variant (G = 32, kernels_s16_wide.cuh).
 struct LengthClass { int logG, R, capacity; bool wide, multi; };
 static const LengthClass kLengthClasses[] = {
-    {3, 4, 32, false, false},    {3, 8, 64, false, false},    {3, 12, 96, false, false},   {3, 16, 128, false, false},
-    {3, 20, 160, false, false},  {3, 24, 192, false, false},  {3, 28, 224, false, false},  {4, 16, 256, false, false},
-    {4, 20, 320, false, false},  {4, 24, 384, false, false},  {4, 28, 448, false, false},  {4, 32, 512, false, false},
-    {5, 20, 640, true, false},   {5, 24, 768, true, false},   {5, 28, 896, true, false},   {5, 32, 1024, true, false},
-    {5, 32, 1024, true, true},
+    {3, 4, 32, false, false}, {3, 6, 48, false, false}, {3, 8, 64, false, false}, {3, 10, 80, false, false},
+    {3, 12, 96, false, false}, {3, 14, 112, false, false}, {3, 16, 128, false, false}, {3, 18, 144, false, false},
+    {3, 20, 160, false, false}, {3, 22, 176, false, false}, {3, 24, 192, false, false}, {3, 26, 208, false, false},
+    {3, 28, 224, false, false}, {3, 30, 240, false, false}, {4, 16, 256, false, false}, {4, 18, 288, false, false},
+    {4, 20, 320, false, false}, {4, 22, 352, false, false}, {4, 24, 384, false, false}, {4, 26, 416, false, false},
+    {4, 28, 448, false, false}, {4, 30, 480, false, false}, {4, 32, 512, false, false}, {5, 18, 576, true, false},
+    {5, 20, 640, true, false}, {5, 22, 704, true, false}, {5, 24, 768, true, false}, {5, 26, 832, true, false},
+    {5, 28, 896, true, false}, {5, 30, 960, true, false}, {5, 32, 1024, true, false}, {5, 32, 1024, true, true},
 };
 constexpr int kNumLengthClasses = sizeof(kLengthClasses) / sizeof(kLengthClasses[0]);
 constexpr int kS16OverflowThreshold = 25000;  // reference MAX_ACC_SHORT, src/kernels.cuh:5
@@ -169,7 +172,7 @@ struct ClassLayout {
     DevBuf<S16Item> items;
 };
 
-constexpr int kMaxClassStreams = 24;
+constexpr int kMaxClassStreams = 32;
 constexpr int kProfileRows = kFused + 63;  // 441 fused-pair rows + two s16 single-residue planes + one int32 plane (array kernels)
 
 struct Shard {
@@ -673,9 +676,13 @@ struct Engine {
                         launch_s16_wide<32, true>(wide, g, strm);
                     } else {
                         switch (lc.R) {
+                            case 18: launch_s16_wide<18, false>(wide, g, strm); break;
                             case 20: launch_s16_wide<20, false>(wide, g, strm); break;
+                            case 22: launch_s16_wide<22, false>(wide, g, strm); break;
                             case 24: launch_s16_wide<24, false>(wide, g, strm); break;
+                            case 26: launch_s16_wide<26, false>(wide, g, strm); break;
                             case 28: launch_s16_wide<28, false>(wide, g, strm); break;
+                            case 30: launch_s16_wide<30, false>(wide, g, strm); break;
                             case 32: launch_s16_wide<32, false>(wide, g, strm); break;
                             default: fail(SW4_ERR_INVALID, "no wide kernel for R=%d", lc.R);
                         }
@@ -684,12 +691,19 @@ struct Engine {
                     narrow.ctaOffset = ctaOffset;
                     switch (lc.R) {
                         case 4: launch_s16<4>(narrow, g, strm); break;
+                        case 6: launch_s16<6>(narrow, g, strm); break;
                         case 8: launch_s16<8>(narrow, g, strm); break;
+                        case 10: launch_s16<10>(narrow, g, strm); break;
                         case 12: launch_s16<12>(narrow, g, strm); break;
+                        case 14: launch_s16<14>(narrow, g, strm); break;
                         case 16: launch_s16<16>(narrow, g, strm); break;
+                        case 18: launch_s16<18>(narrow, g, strm); break;
                         case 20: launch_s16<20>(narrow, g, strm); break;
+                        case 22: launch_s16<22>(narrow, g, strm); break;
                         case 24: launch_s16<24>(narrow, g, strm); break;
+                        case 26: launch_s16<26>(narrow, g, strm); break;
                         case 28: launch_s16<28>(narrow, g, strm); break;
+                        case 30: launch_s16<30>(narrow, g, strm); break;
                         case 32: launch_s16<32>(narrow, g, strm); break;
                         default: fail(SW4_ERR_INVALID, "no kernel for R=%d", lc.R);
                     }

@@ -107,6 +107,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src));
 }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -133,7 +136,7 @@ __device__ __forceinline__ void ring_fill(uint32_t ringBase, const uint32_t* __r
 // R = register columns per lane.
 template <int R>
 __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params prm) {
-    static_assert(R % 4 == 0, "a lane's staging slice (R u16 codes) must be a whole number of 8-byte chunks");
+    static_assert(R % 2 == 0, "a lane's staging slice (R u16 codes) must be a whole number of 4-byte words");
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned long long tStart;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tStart));
@@ -207,9 +210,12 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
             if constexpr ((R * 2) % 16 == 0) {
 #pragma unroll
                 for (int i = 0; i < R * 2 / 16; i++) cp_async16(stageLane + i * 16, src + i * 16);
-            } else {
+            } else if constexpr ((R * 2) % 8 == 0) {
 #pragma unroll
                 for (int i = 0; i < R * 2 / 8; i++) cp_async8(stageLane + i * 8, src + i * 8);
+            } else {
+#pragma unroll
+                for (int i = 0; i < R * 2 / 4; i++) cp_async4(stageLane + i * 4, src + i * 4);
             }
         }
         cp_async_commit();

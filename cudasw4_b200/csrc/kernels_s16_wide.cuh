@@ -61,7 +61,7 @@ __device__ __forceinline__ void ring_fill_wide(uint32_t ringBase, const uint32_t
 // R = register columns per lane. MULTI = the long class: G must be 32 and an item may span several segments.
 template <int R, bool MULTI>
 __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_wide_kernel(const S16WideParams prm) {
-    static_assert(R % 4 == 0, "a lane's staging slice (R u16 codes) must be a whole number of 8-byte chunks");
+    static_assert(R % 2 == 0, "a lane's staging slice (R u16 codes) must be a whole number of 4-byte words");
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned long long tStart;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tStart));
@@ -135,9 +135,12 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_wide_kernel(const S16Wi
             if constexpr ((R * 2) % 16 == 0) {
 #pragma unroll
                 for (int i = 0; i < R * 2 / 16; i++) cp_async16(stageLane + i * 16, src + i * 16);
-            } else {
+            } else if constexpr ((R * 2) % 8 == 0) {
 #pragma unroll
                 for (int i = 0; i < R * 2 / 8; i++) cp_async8(stageLane + i * 8, src + i * 8);
+            } else {
+#pragma unroll
+                for (int i = 0; i < R * 2 / 4; i++) cp_async4(stageLane + i * 4, src + i * 4);
             }
         }
         cp_async_commit();
