@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsw4b200.so")
+LIB_PATH = os.environ.get("SW4B200_LIB") or os.path.join(_HERE, "libsw4b200.so")  # override: kernel-variant sweeps only
 
 EXPORTS = [
     "sw4_create", "sw4_destroy", "sw4_last_error", "sw4_set_gap_scores", "sw4_set_num_top", "sw4_set_blosum",

@@ -115,6 +115,19 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 constexpr int kGroupStateInts = 8;  // per-group bookkeeping kept in shared memory (touched at restarts only)
 
+// Software-pipeline depth of the substitution loads (columns fetched ahead of their use) per instantiation: ptxas'
+// schedule is sensitive to it (tools/class_sweep.py measures every class; SW4_S16_PREFETCH overrides for such sweeps).
+template <int R>
+__host__ __device__ constexpr int s16_prefetch_depth() {
+#ifdef SW4_S16_PREFETCH
+    return SW4_S16_PREFETCH;
+#else
+    // measured per instantiation (B200, q = 1000, G = 16, depths 5..16): R = 20: 6 -> 7.04 vs 6.53 TCUPS at 8..14;
+    // R = 24: 14 -> 6.94 vs 6.76; R = 30: 14 -> 7.02 vs 6.75; R = 32: 7 -> 6.78 vs 6.69; elsewhere 10 is at the top
+    return R == 20 ? 6 : (R == 24 || R == 28 || R == 30) ? 14 : R == 32 ? 7 : 10;
+#endif
+}
+
 template <int R>
 constexpr int s16_smem_bytes() { return kRingBytes + kS16Warps * 32 * R * 2 + kS16Warps * 4 * kGroupStateInts * 4; }
 
@@ -313,7 +326,7 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
                 // substitution words are fetched kPrefetch columns ahead of their use: an explicit software pipeline, because
                 // how far ptxas hoists the loads on its own varies with unrelated source changes (measured on the 1M x 256
                 // benchmark: distance 1..4: 6.47, 5: 6.69, 8..16: 6.85 TCUPS for R = 32; 6.82 -> 6.89 for R = 16)
-                constexpr int kPrefetch = 10;
+                constexpr int kPrefetch = s16_prefetch_depth<R>();
                 uint2 sq[kPrefetch + 1];
 #pragma unroll
                 for (int c = 0; c <= kPrefetch && c < R; c++) sq[c] = lds_u64_imm<i * 8>(colAddr[c]);

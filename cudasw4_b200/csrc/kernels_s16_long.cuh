@@ -252,7 +252,11 @@ __global__ void __launch_bounds__(kLongMaxWarps * 32, 1) sw_s16_long_kernel(cons
                     if (lane == 0) { Hin = useBorder ? bd.x : 0u; Ein = useBorder ? bd.y : NEG2; }
                     if (!realRow) { Hin = 0; Ein = NEG2; }
                     uint32_t E = Ein;
+#ifdef SW4_LONG_PREFETCH
+                    constexpr int kPrefetch = SW4_LONG_PREFETCH;
+#else
                     constexpr int kPrefetch = 6;
+#endif
                     uint32_t q0[kPrefetch + 1], q1[kPrefetch + 1];
 #pragma unroll
                     for (int c = 0; c <= kPrefetch && c < R; c++) {
