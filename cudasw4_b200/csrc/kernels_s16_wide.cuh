@@ -37,6 +37,16 @@ struct S16WideParams {
     int borderStride;
 };
 
+// software-pipeline depth of the substitution loads per instantiation (see s16_prefetch_depth)
+template <int R>
+__host__ __device__ constexpr int s16_wide_prefetch_depth() {
+#ifdef SW4_WIDE_PREFETCH
+    return SW4_WIDE_PREFETCH;
+#else
+    return R == 24 ? 12 : R == 28 ? 14 : 8;  // measured (tools/class_sweep.py): R = 28: 6.49 vs 6.30 TCUPS, R = 24: 6.60 vs 6.53
+#endif
+}
+
 template <int R>
 constexpr int s16_wide_smem_bytes() { return kRingBytes + kS16Warps * 32 * R * 2 + kS16Warps * 8 * kGroupStateInts * 4; }
 
@@ -252,7 +262,7 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_wide_kernel(const S16Wi
                 uint32_t E = Ein;
                 // substitution words are fetched kPrefetch columns ahead of their use (explicit software pipeline, see
                 // kernels_s16.cuh)
-                constexpr int kPrefetch = 8;
+                constexpr int kPrefetch = s16_wide_prefetch_depth<R>();
                 uint32_t sq[kPrefetch + 1];
 #pragma unroll
                 for (int c = 0; c <= kPrefetch && c < R; c++) sq[c] = lds_u32_imm<i * 4>(colAddr[c]);
