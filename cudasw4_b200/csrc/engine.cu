@@ -663,6 +663,7 @@ struct Engine {
             if (lc.wide) {
                 fillCommon(wide);
                 wide.period = s16WidePeriod(qlen, G);
+                wide.lengths = sh.dLengths.p;
                 wide.border = sh.dBorderWide.p;
                 wide.borderStride = (int)sh.borderWideStride;
             } else {

@@ -113,6 +113,9 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// the reference counts "overflows" only in its partition 34 (240 < len <= 8000, src/cudasw4.cuh:2152-2169): longer
+// subjects go straight to its 32-bit kernel
+constexpr int kStatMaxLength = 8000;
 constexpr int kGroupStateInts = 8;  // per-group bookkeeping kept in shared memory (touched at restarts only)
 
 // Software-pipeline depth of the substitution loads (columns fetched ahead of their use) per instantiation: ptxas'

@@ -132,14 +132,14 @@ __global__ void __launch_bounds__(kLongMaxWarps * 32, 1) sw_s16_long_kernel(cons
                 if (sub0 >= 0) {
                     const int best = max(atomicMax(prm.scores + sub0, lo), lo);
                     if (isLast) {  // blocks of a pair finish in stream order: this is the pair's final score
-                        if (best >= prm.statThreshold) atomicAdd(prm.statCount, 1);
+                        if (best >= prm.statThreshold && prm.lengths[sub0] <= kStatMaxLength) atomicAdd(prm.statCount, 1);
                         if (best >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = sub0;
                     }
                 }
                 if (sub1 >= 0) {
                     const int best = max(atomicMax(prm.scores + sub1, hi), hi);
                     if (isLast) {
-                        if (best >= prm.statThreshold) atomicAdd(prm.statCount, 1);
+                        if (best >= prm.statThreshold && prm.lengths[sub1] <= kStatMaxLength) atomicAdd(prm.statCount, 1);
                         if (best >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = sub1;
                     }
                 }

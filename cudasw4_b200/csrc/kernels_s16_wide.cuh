@@ -33,6 +33,7 @@ struct S16WideParams {
     int activeGroups;            // groups per CTA that take work (fewer than all when the class cannot fill its SMs: the
                                  // items are then spread over more SMs and every warp gets a larger share of its scheduler)
     int ctaOffset;               // index of this launch's first CTA within the class (a class may be split in two launches)
+    const int32_t* lengths;      // MULTI only: [numLocalSubjects] (subjects longer than kStatMaxLength are not counted)
     uint2* border;               // MULTI only: [gridWarps][borderStride] (H, E) of a segment's last column per query row
     int borderStride;
 };
@@ -194,12 +195,12 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_wide_kernel(const S16Wi
                         const int s0 = gs[0], s1 = gs[1];
                         const int lo = (int)(short)(r & 0xffff), hi = (int)(short)(r >> 16);
                         if (s0 >= 0) {
-                            if (lo >= prm.statThreshold) atomicAdd(prm.statCount, 1);
+                            if (lo >= prm.statThreshold && (!MULTI || prm.lengths[s0] <= kStatMaxLength)) atomicAdd(prm.statCount, 1);
                             if (lo >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = s0;
                             prm.scores[s0] = lo;
                         }
                         if (s1 >= 0) {
-                            if (hi >= prm.statThreshold) atomicAdd(prm.statCount, 1);
+                            if (hi >= prm.statThreshold && (!MULTI || prm.lengths[s1] <= kStatMaxLength)) atomicAdd(prm.statCount, 1);
                             if (hi >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = s1;
                             prm.scores[s1] = hi;
                         }

@@ -184,6 +184,36 @@ def test_scores_beyond_16_bit_are_exact(oracle):
             assert res.scores == s.tolist() and res.referenceIds == i.tolist()
 
 
+def test_many_saturating_subjects_and_overflow_count(oracle):
+    """More 16-bit overflows than SMs (the exact array kernel streams several subjects per CTA), long and short
+    subjects among them; stats.numOverflows follows the reference: subjects of 241..8000 residues whose exact score
+    reaches 25000 (longer ones go straight to its 32-bit kernel, src/cudasw4.cuh:2152-2169)."""
+    rng = np.random.default_rng(33)
+    q = synth.random_residues(rng, 5600)
+    q[::4] = 17  # W scores 11: lifts the self score well above 25000
+    seqs = [synth.mutate(rng, q, 0.02 + 0.002 * (i % 40)) for i in range(330)]
+    seqs += [np.concatenate([synth.random_residues(rng, 1500), q, synth.random_residues(rng, 3000)]) for _ in range(6)]  # > 8000
+    seqs += [q[:4000].copy(), q[1000:4800].copy()]
+    seqs += [synth.random_residues(rng, int(n)) for n in rng.integers(300, 6000, 150)]
+    db = dbformat.from_sequences(seqs)
+    with _engine(numTop=20, blosumType=62) as eng:
+        eng.setDatabase(db)
+        for rep in range(2):
+            res = eng.scan(dbformat.decode(q))
+            scores, ids = eng.lastScanAllScores()
+            got = np.empty(db.num_sequences, np.int32)
+            got[ids] = scores
+            ref = oracle.scan(62, q, db, -11, -1)
+            bad = np.nonzero(got != ref)[0]
+            assert len(bad) == 0, (rep, bad[:8], got[bad[:8]], ref[bad[:8]], db.lengths[bad[:8]])
+            s, i = oracle.topk(ref, 20)
+            assert res.scores == s.tolist() and res.referenceIds == i.tolist()
+            L = db.lengths
+            expect = int(((ref >= 25000) & (L > 240) & (L <= 8000)).sum())
+            assert expect > 300 and int((ref >= 25000).sum()) > expect
+            assert res.stats.numOverflows == expect
+
+
 def test_many_long_subjects_repeated_scans(oracle):
     """Enough multi-segment subjects to spread the long class over many (and an odd number of) SMs, scanned several
     times with different queries: every score must match the oracle every time (no stale or shared border state)."""
