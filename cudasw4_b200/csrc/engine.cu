@@ -239,9 +239,10 @@ struct Shard {
 // no lane of a half-warp starts before step 0
 // The 256-column class can run as 16 lanes x 16 columns or as 8 lanes x 32 columns on the same pair-blocks (a block is
 // 256 consecutive column codes either way). 8 x 32 has 8 fewer fill steps per alignment, 16 x 16 the better steady state
-// (fewer live registers): short queries take the former (measured cross-over between q = 600 and 700).
+// (fewer live registers): short queries take the former (measured cross-over between q = 1000 and 1500).
 static inline LengthClass shapeForQuery(const LengthClass& lc, int qlen) {
-    if (lc.capacity == 256 && !lc.wide && qlen < 640) return LengthClass{3, 32, 256, false, false};
+    static const int crossover = [] { const char* e = getenv("SW4_CLASS256_CROSSOVER"); return e ? atoi(e) : 1200; }();
+    if (lc.capacity == 256 && !lc.wide && qlen < crossover) return LengthClass{3, 32, 256, false, false};
     return lc;
 }
 
@@ -529,7 +530,9 @@ struct Engine {
             sh.hTopCap = topWords + 64;
             SW4_CUDA(cudaMallocHost(&sh.hTop, sh.hTopCap * sizeof(int32_t)));
         }
-        const int profStride = (qlen + 64 + 3) / 4 * 4;  // >= 2 * period of any class
+        // rows of the positional profile start on 128-byte lines: the ring refill copies 64 contiguous bytes per row, which
+        // then always fall into two sectors of one line (a stride of 4 mod 8 words cost 3-4 % on the peak benchmark)
+        const int profStride = (qlen + 64 + 31) / 32 * 32;
         // All device scratch is sized here, BEFORE the timed region, for a query capacity that only grows by doubling:
         // cudaMalloc/cudaFree inside the event-bracketed region stall the stream for up to hundreds of milliseconds.
         if (qlen > sh.queryCapacity || k > sh.topCapacity) {
@@ -538,7 +541,7 @@ struct Engine {
             while (cap < qlen) cap *= 2;
             sh.queryCapacity = cap;
             sh.topCapacity = std::max(sh.topCapacity, std::max(k, 64));
-            const size_t capStride = (size_t)(cap + 64 + 3) / 4 * 4;
+            const size_t capStride = (size_t)(cap + 64 + 31) / 32 * 32;
             sh.dQueryLetters.ensure((size_t)cap + 16);
             sh.dQueryCodes.ensure((size_t)cap + 16);
             sh.dProfile.ensure((size_t)kProfileRows * capStride);
