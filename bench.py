@@ -258,7 +258,8 @@ def main():
                          "frac": kernel_gcups / peak_gcups,
                          "peak_model": f"{sms} SMs x 4 schedulers x 64 cells / 7 clk (3.5 DPX ALU-pipe ops per s16x2 cell-pair at "
                                        f"1 warp-inst / 2 clk, measured) x {sm_hz/1e6:.0f} MHz (nvidia-smi under load)",
-                         "traffic": _traffic(),
+                         "traffic": (_traffic() or {}).get("dram_bytes_read_plus_write_per_launch"),
+                         "traffic_detail": _traffic(),
                          "hbm": {"achieved": hbm_bytes / 1e9 / ker_s, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                  "frac": hbm_bytes / 1e9 / ker_s / peaks.get("hbm_gbs", 6650.0), "peak_source": peak_src,
                                  "note": "database streaming only; the path is compute bound (1/len_query bytes per cell)"}},
