@@ -248,7 +248,8 @@ __global__ void __launch_bounds__(kLongMaxWarps * 32, 1) sw_s16_long_kernel(cons
                     uint32_t Hin = __shfl_up_sync(0xffffffffu, Hp[R - 1], 1);
                     uint32_t Ein = __shfl_up_sync(0xffffffffu, Elast, 1);
                     const bool realRow = (unsigned)p < (unsigned)prm.qlen;
-                    const uint2 bd = lds_u64(fifoIn + (p & (kLongFifoRows - 1)) * 8);
+                    uint2 bd = make_uint2(0u, 0u);  // only the first lane's real rows read the FIFO (the slot is then final)
+                    if (lane == 0 && realRow) bd = lds_u64(fifoIn + (p & (kLongFifoRows - 1)) * 8);
                     if (lane == 0) { Hin = useBorder ? bd.x : 0u; Ein = useBorder ? bd.y : NEG2; }
                     if (!realRow) { Hin = 0; Ein = NEG2; }
                     uint32_t E = Ein;

@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(kLongMaxWarps * 32, 1) sw_s32_long_kernel(cons
                     int Hin = __shfl_up_sync(0xffffffffu, Hp[R - 1], 1);
                     int Ein = __shfl_up_sync(0xffffffffu, Elast, 1);
                     const bool realRow = (unsigned)p < (unsigned)prm.qlen;
-                    const uint2 bd = lds_u64(fifoIn + (p & (kLongFifoRows - 1)) * 8);
+                    uint2 bd = make_uint2(0u, 0u);  // only the first lane's real rows read the FIFO (the slot is then final)
+                    if (lane == 0 && realRow) bd = lds_u64(fifoIn + (p & (kLongFifoRows - 1)) * 8);
                     if (lane == 0) { Hin = useBorder ? (int)bd.x : 0; Ein = useBorder ? (int)bd.y : kNegS32; }
                     if (!realRow) { Hin = 0; Ein = kNegS32; }
                     int E = Ein;
