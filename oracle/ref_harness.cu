@@ -29,6 +29,7 @@
 #include <cstdint>
 #include <string_view>
 #include <type_traits>
+#include <omp.h>
 #include <thrust/device_vector.h>
 #include <thrust/sort.h>
 #include <thrust/merge.h>
@@ -47,6 +48,21 @@ int ref_cpu_gotoh_blosum62(const char* q_codes, const char* s_codes, int qlen, i
     alignas(alignof(cudasw4::CudaSW4)) static unsigned char storage[sizeof(cudasw4::CudaSW4)];
     auto* self = reinterpret_cast<cudasw4::CudaSW4*>(storage);
     return self->affine_local_DP_host_protein_blosum62_converted(q_codes, s_codes, qlen, slen, gop, gex);
+}
+
+// All subjects of a makedb-layout block against one query with the reference's own scalar routine, one OpenMP task per
+// subject: the structure of its computeAllScoresCPU_blosum62 (src/cudasw4.cuh:767-796). Returns the threads used.
+// (bench.py's CPU arm: "kind": "reference".)
+int ref_cpu_scan_blosum62(const char* q_codes, int qlen, const char* chars, const size_t* offsets, const int* lengths, long n,
+                          int gop, int gex, int* out, int threads){
+    alignas(alignof(cudasw4::CudaSW4)) static unsigned char storage[sizeof(cudasw4::CudaSW4)];
+    auto* self = reinterpret_cast<cudasw4::CudaSW4*>(storage);
+    if(threads <= 0) threads = omp_get_max_threads();
+    #pragma omp parallel for schedule(dynamic, 16) num_threads(threads)
+    for(long i = 0; i < n; i++){
+        out[i] = self->affine_local_DP_host_protein_blosum62_converted(q_codes, chars + offsets[i], qlen, lengths[i], gop, gex);
+    }
+    return threads;
 }
 
 // type: 45, 50, 62, 80 -> the 21x21 "_20" table the shipped align uses (CAN_USE_FULL_BLOSUM is off)

@@ -128,3 +128,22 @@ def test_oracle_properties(oracle):
     m = oracle.matrix(62)
     assert oracle.score(62, q, q, -11, -1) == sum(int(m[c, c]) for c in q)
     assert oracle.score(62, q, np.zeros(0, np.uint8), -11, -1) == 0
+
+
+def test_oracle_scan_matches_reference_cpu_routine_live(oracle):
+    """When oracle/_ref/libref_harness.so is present (built from /root/reference by oracle/Makefile; it travels to the GPU
+    box), the oracle's scan must equal the reference's own scalar CPU Gotoh on a fresh random database, subject by
+    subject (the committed fixtures in tests/golden/ref_cpu_gotoh.json pin the same routine on fixed inputs)."""
+    import os
+    import bench
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_harness.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_harness.so not built here")
+    ref = bench._ReferenceCpuScan(path)
+    rng = np.random.default_rng(123)
+    seqs = [synth.random_residues(rng, int(n)) for n in rng.integers(1, 900, 1500)]
+    seqs += [np.full(40, 20, np.uint8), synth.random_residues(rng, 2500)]
+    db = dbformat.from_sequences(seqs)
+    for ql, (gop, gex) in zip((1, 37, 400), ((-11, -1), (-5, -3), (-11, -1))):
+        q = synth.random_residues(rng, ql)
+        assert (ref.scan(62, q, db, gop, gex) == oracle.scan(62, q, db, gop, gex)).all()
