@@ -45,3 +45,29 @@ def test_product_never_imports_the_oracle():
                 assert "liboracle" not in src and "sw4o_" not in src and "oracle_lib" not in src, fn
     for fn in os.listdir(os.path.join(ROOT, "include")):
         assert "sw4o_" not in open(os.path.join(ROOT, "include", fn)).read()
+
+
+def test_headers_compile_standalone(tmp_path):
+    """include/sw4b200.h is plain C (no C++ / CUDA / torch types in the ABI); include/cudasw4.cuh, the source-compatible
+    mirror of the reference's host class (src/cudasw4.cuh:244-2454), compiles with a host compiler alone."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "include")
+    gcc, gxx = shutil.which("gcc"), "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if not gcc or not gxx:
+        pytest.skip("no host compiler")
+    c_src = tmp_path / "abi.c"
+    c_src.write_text('#include "sw4b200.h"\nint main(void) { sw4_handle* h = 0; (void)h; return sw4_version() == 0; }\n')
+    r = subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(c_src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cpp_src = tmp_path / "facade.cpp"
+    cpp_src.write_text('#include "cudasw4.cuh"\n'
+                       'int main() {\n'
+                       '  cudasw4::KernelTypeConfig k; cudasw4::MemoryConfig m;\n'
+                       '  cudasw4::CudaSW4 sw({0}, 10, cudasw4::BlosumType::BLOSUM62_20, k, m, false);\n'
+                       '  sw.setGapOpenScore(-11); sw.setGapExtendScore(-1);\n'
+                       '  cudasw4::ScanResult r = sw.scan("ACDE", 4); return (int)r.scores.size();\n'
+                       '}\n')
+    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-I", inc, str(cpp_src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
