@@ -307,6 +307,7 @@ struct Engine {
     // scheduling of the length classes (development switches: SW4_SCHED=partition|backfill, SW4_BACKFILL_ITEMS=n)
     bool backfill = [] { const char* e = getenv("SW4_SCHED"); return !(e && std::string(e) == "partition"); }();
     bool useLongKernel = [] { const char* e = getenv("SW4_NO_LONG_KERNEL"); return !e; }();
+    int longMinWarps = [] { const char* e = getenv("SW4_LONG_MIN_WARPS"); return e ? std::max(2, atoi(e)) : 2; }();
     int backfillItems = [] { const char* e = getenv("SW4_BACKFILL_ITEMS"); return e ? std::max(1, atoi(e)) : 4; }();
     int shardRank = 0, shardWorld = 1;
     std::unique_ptr<HostDB> db;
@@ -721,7 +722,7 @@ struct Engine {
                 const int p0 = (qlen + 32 + 15) / 16 * 16;
                 longWarps = kLongMaxWarps;
                 while (longWarps > 1 && kLongLag * longWarps + 64 > p0) longWarps >>= 1;
-                if (longWarps < 2) longWarps = 0;
+                if (longWarps < longMinWarps) longWarps = 0;
                 if (longWarps) {
                     S16LongParams lp{};
                     lp.cols = cl.cols.p;
