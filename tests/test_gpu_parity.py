@@ -146,6 +146,29 @@ def test_planted_homologs_and_ties(oracle):
             assert "hom_q%d_" % qi in eng.getReferenceHeader(res.referenceIds[0])
 
 
+def test_c1_full_config_all_queries(oracle):
+    """BASELINE.json configs[0] / SURVEY.md 8(d) C1 at full size: 10,130 sequences (lognormal lengths, planted homologs,
+    exact duplicates => score ties, non-standard letters), all 20 queries, BLOSUM62 -11/-1, top-10: every score and the
+    top-10 list (ties by DB id) against the oracle (1.4e11 cells: ~15 s of CPU on the box's 16 cores)."""
+    recs, queries = synth.config_c1(seed=1, n=10_000)
+    db = dbformat.from_sequences([dbformat.encode(s) for _, s in recs], [h for h, _ in recs])
+    with _engine(numTop=10, blosumType=62) as eng:
+        eng.setDatabase(db)
+        for qi, (_, q) in enumerate(queries):
+            qc = dbformat.encode(q)
+            res = eng.scan(q)
+            scores, ids = eng.lastScanAllScores()
+            got = np.empty(db.num_sequences, np.int32)
+            got[ids] = scores
+            ref = oracle.scan(62, qc, db, -11, -1)
+            bad = np.nonzero(got != ref)[0]
+            assert len(bad) == 0, (qi, bad[:8], got[bad[:8]], ref[bad[:8]], db.lengths[bad[:8]])
+            s, i = oracle.topk(ref, 10)
+            assert res.scores == s.tolist() and res.referenceIds == i.tolist(), qi
+            L = db.lengths
+            assert res.stats.numOverflows == int(((ref >= 25000) & (L > 240) & (L <= 8000)).sum()), qi
+
+
 def test_long_query_against_short_subjects(oracle):
     """Query much longer than the subjects (long periods, many ring refills per alignment), odd and even lengths."""
     rng = np.random.default_rng(77)
