@@ -11,19 +11,29 @@ HDRS     := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.hpp) include/sw4b200.h
 .PHONY: all lib cli oracle clean
 all: lib cli
 
+# one object per kernel family so that they build in parallel (make -j) and independently of the host engine
+UNITS    := engine launch_s16 launch_s16_wide launch_long
+OBJS     := $(patsubst %,build/%.o,$(UNITS))
+
 lib: $(LIB)
-$(LIB): $(CSRC)/engine.cu $(HDRS)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/engine.cu -lpthread 2> build/engine.ptxas.log || (cat build/engine.ptxas.log; exit 1)
-	@grep -E "error|spill" build/engine.ptxas.log | sort | uniq -c | sort -rn | head -20 || true
+build/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lpthread
+	@cat $(patsubst %,build/%.ptxas.log,$(UNITS)) > build/engine.ptxas.log
+	@grep -E "error|spill" build/engine.ptxas.log | grep -v " 0 bytes spill stores, 0 bytes spill loads" | sort | uniq -c | sort -rn | head -20 || true
 
 cli: build/align build/makedb
 build/align: $(CSRC)/cli_align.cpp include/cudasw4.cuh include/sw4b200.h $(CSRC)/fasta_reader.hpp $(LIB)
+	@mkdir -p build
 	$(CXXHOST) -std=c++17 -O2 -Wall -Iinclude -o $@ $(CSRC)/cli_align.cpp -Lcudasw4_b200 -lsw4b200 -Wl,-rpath,'$$ORIGIN/../cudasw4_b200' -lz
 build/makedb: $(CSRC)/cli_makedb.cpp $(CSRC)/fasta_reader.hpp
+	@mkdir -p build
 	$(CXXHOST) -std=c++17 -O2 -Wall -o $@ $(CSRC)/cli_makedb.cpp -lz
 
 oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -f $(LIB) build/align build/makedb build/*.log
+	rm -f $(LIB) build/align build/makedb build/*.log build/*.o

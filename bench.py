@@ -11,6 +11,16 @@ A *step* = one pass of the hot path over the whole query batch: all 20 queries s
 Weak scaling: every rank holds 1,000,000 subjects (shard `rank` of a N x 1M-subject database, global ids); the only
 exchange is an all_gather of k (score, id) pairs per rank per query, merged on rank 0.
 
+Two more legs run after the timed region of the headline metric (they never change `value`):
+  c4           STRONG scaling on ONE fixed UniRef50-shaped database (C4: 65,000,000 subjects / 17.0 G residues, seed 4,
+               sw4_set_pseudo_database_lengths): every rank generates and uploads only its own shard (blocks of 256
+               subjects, rank, rank+N, ...), queries 0/5/9/14/19, one pass, per-query GCUPS = cells / max-over-ranks
+               device time; `checked` = planted copies found with their self score and a >= 3,000-subject sample of
+               every rank's scores equal to the CPU oracle (the reference's multi-GPU use, rununiref50benchmark.sh).
+  ref_gpu      the reference's OWN align binary (oracle/_ref/align, built for sm_100a from /root/reference), --dpx and
+               default half2 kernels, on the same PseudoDB (runpeakbenchmark.sh:27,44-50), timed on the same GPU
+               right after ours (rank 0, N = 1 only).
+
   value        GCUPS from the device-timed scan regions (CUDA events inside libsw4b200.so on its own stream, the
                reference's own "Scan time" definition, src/cudasw4.cuh:707-726), max over ranks
   e2e          GCUPS from host wall-clock around the same C-ABI calls with HOST query buffers (pinned staging, H2D,
@@ -128,10 +138,20 @@ def _cpu_scanner():
     return oracle_lib.load(), "port"
 
 
+def host_threads() -> int:
+    """Threads for the CPU arm: every core this process may run on. (torchrun exports OMP_NUM_THREADS=1, which would
+    silently turn an `omp_get_max_threads()` default into a 1-core baseline.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(seconds_budget: float = 20.0, threads: int = 0):
     """CPU Gotoh (the reference's own scalar routine if built, else the oracle port; OpenMP over subjects) on a bounded
     sample of the same workload."""
     import numpy as np
+    threads = threads or host_threads()
     from cudasw4_b200 import dbformat, synth
     oracle, kind = _cpu_scanner()
     queries = [dbformat.encode(s) for _, s in synth.load_queries()]

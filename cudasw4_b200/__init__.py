@@ -101,6 +101,8 @@ class CudaSW4:
         if rc != 0:
             raise SW4Error(rc, (self._lib.sw4_last_error(None) or b"").decode())
         self.numTop = int(numTop)
+        self._gop = -11 if gop is None else int(gop)
+        self._gex = -1 if gex is None else int(gex)
         if kernelTypeConfig is not None:
             self.setKernelTypeConfig(kernelTypeConfig)
 
@@ -129,16 +131,14 @@ class CudaSW4:
 
     # -- configuration (reference src/cudasw4.cuh:539-611) --------------------------------------------------------
     def setGapOpenScore(self, score: int):
-        self._gop = int(score)
-        self._check(self._lib.sw4_set_gap_scores(self._h, self._gop, getattr(self, "_gex", -1)))
+        self.setGapScores(int(score), self._gex)
 
     def setGapExtendScore(self, score: int):
-        self._gex = int(score)
-        self._check(self._lib.sw4_set_gap_scores(self._h, getattr(self, "_gop", -11), self._gex))
+        self.setGapScores(self._gop, int(score))
 
     def setGapScores(self, gop: int, gex: int):
-        self._gop, self._gex = int(gop), int(gex)
-        self._check(self._lib.sw4_set_gap_scores(self._h, self._gop, self._gex))
+        self._check(self._lib.sw4_set_gap_scores(self._h, int(gop), int(gex)))
+        self._gop, self._gex = int(gop), int(gex)  # only after the library accepted them
 
     def setBlosum(self, blosumType):
         self._check(self._lib.sw4_set_blosum(self._h, int(blosumType)))
@@ -150,6 +150,10 @@ class CudaSW4:
     def setKernelTypeConfig(self, val: KernelTypeConfig):
         self._check(self._lib.sw4_set_kernel_types(self._h, int(val.singlePassType), int(val.manyPassType_small),
                                                    int(val.manyPassType_large), int(val.overflowType)))
+
+    def setMemoryConfig(self, val: MemoryConfig):
+        mem = _lib.MemConfig(val.maxBatchBytes, val.maxBatchSequences, val.maxTempBytes, min(val.maxGpuMem, 2**64 - 1))
+        self._check(self._lib.sw4_set_mem_config(self._h, ctypes.byref(mem)))
 
     def setShard(self, rank: int, world: int):
         """One process per GPU: scan only shard `rank` of `world`; ids stay global (no reference equivalent: the
@@ -174,9 +178,37 @@ class CudaSW4:
                                                       lengths.ctypes.data, headers.ctypes.data, hoff.ctypes.data,
                                                       len(lengths)))
 
+    def setDatabaseShard(self, db, globalIds, numSequencesGlobal: int):
+        """One process per GPU, every rank holding only its own shard in host memory: `db` (dbformat.SequenceDB,
+        ascending length) are the local sequences, `globalIds` their (strictly ascending) ids in the whole database."""
+        chars = np.ascontiguousarray(db.chars, dtype=np.uint8)
+        offsets = np.ascontiguousarray(db.offsets, dtype=np.uint64)
+        lengths = np.ascontiguousarray(db.lengths, dtype=np.int32)
+        gids = np.ascontiguousarray(globalIds, dtype=np.int32)
+        if len(gids) != len(lengths):
+            raise ValueError("one global id per local sequence")
+        self._keep = (chars, offsets, lengths, gids)
+        self._check(self._lib.sw4_set_database_shard_memory(self._h, chars.ctypes.data, offsets.ctypes.data, lengths.ctypes.data,
+                                                            None, None, len(lengths), gids.ctypes.data, int(numSequencesGlobal)))
+
     def setPseudoDatabase(self, num: int, length: int, seed: int = 42):
         """loadPseudoDB(num, length) + setDatabase (reference src/dbdata.hpp:219-272, src/main.cu:193-203)."""
         self._check(self._lib.sw4_set_pseudo_database(self._h, int(num), int(length), int(seed)))
+        self._keep = None
+
+    def setPseudoDatabaseLengths(self, lengths, seed: int, planted: dict | None = None):
+        """Synthetic database with the given (ascending) length array; this handle generates its own shard only
+        (setShard). `planted` maps a global id to the residue codes that replace that sequence (same length)."""
+        L = np.ascontiguousarray(lengths, dtype=np.int32)
+        planted = planted or {}
+        ids = np.array(sorted(planted), dtype=np.int32)
+        codes = [np.ascontiguousarray(planted[int(i)], dtype=np.uint8) for i in ids]
+        for i, c in zip(ids, codes):
+            if len(c) != int(L[i]):
+                raise ValueError(f"planted sequence {i} has length {len(c)}, slot has {int(L[i])}")
+        ptrs = (ctypes.c_void_p * max(1, len(codes)))(*[c.ctypes.data for c in codes])
+        self._check(self._lib.sw4_set_pseudo_database_lengths(self._h, L.ctypes.data, len(L), int(seed) & (2**64 - 1),
+                                                              ids.ctypes.data if len(ids) else None, ptrs, len(codes)))
         self._keep = None
 
     def prefetchDBToGpus(self):
@@ -196,6 +228,27 @@ class CudaSW4:
                                        ctypes.byref(st)))
         c = int(count.value)
         return ScanResult(scores[:c].tolist(), ids[:c].tolist(), _stats(st))
+
+    def scanMany(self, queries):
+        """Query batching (sw4_scan_many): all `queries` (letters) with several scans in flight per GPU. Returns
+        (list of ScanResult in query order, BenchmarkStats of the whole call: device-timed span, total GCUPS)."""
+        qs = [q.encode() if isinstance(q, str) else bytes(q) for q in queries]
+        nq = len(qs)
+        k = max(self.numTop, 1)
+        arr = (ctypes.c_char_p * max(nq, 1))(*qs)
+        lens = (ctypes.c_int32 * max(nq, 1))(*[len(q) for q in qs])
+        scores = np.empty((max(nq, 1), k), dtype=np.int32)
+        ids = np.empty((max(nq, 1), k), dtype=np.int32)
+        counts = np.zeros(max(nq, 1), dtype=np.int32)
+        per = (_lib.Stats * max(nq, 1))()
+        total = _lib.Stats()
+        self._check(self._lib.sw4_scan_many(self._h, arr, lens, nq, scores.ctypes.data, ids.ctypes.data, counts.ctypes.data,
+                                            per, ctypes.byref(total)))
+        out = []
+        for i in range(nq):
+            c = int(counts[i]) if self.numTop > 0 else 0
+            out.append(ScanResult(scores[i, :c].tolist(), ids[i, :c].tolist(), _stats(per[i])))
+        return out, _stats(total)
 
     def lastScanAllScores(self):
         """(scores, global ids) of every subject this handle scanned in the last scan() (parity helper)."""

@@ -9,8 +9,9 @@ LIB_PATH = os.environ.get("SW4B200_LIB") or os.path.join(_HERE, "libsw4b200.so")
 
 EXPORTS = [
     "sw4_create", "sw4_destroy", "sw4_last_error", "sw4_set_gap_scores", "sw4_set_num_top", "sw4_set_blosum",
-    "sw4_set_kernel_types", "sw4_set_shard", "sw4_set_database_files", "sw4_set_database_memory",
-    "sw4_set_pseudo_database", "sw4_upload_database", "sw4_scan", "sw4_last_scan_all_scores", "sw4_reference_header",
+    "sw4_set_kernel_types", "sw4_set_mem_config", "sw4_set_shard", "sw4_set_database_files", "sw4_set_database_memory",
+    "sw4_set_database_shard_memory", "sw4_set_pseudo_database", "sw4_set_pseudo_database_lengths", "sw4_upload_database", "sw4_scan", "sw4_scan_many",
+    "sw4_last_scan_all_scores", "sw4_reference_header",
     "sw4_reference_length", "sw4_reference_sequence", "sw4_total_timer_start", "sw4_total_timer_stop",
     "sw4_get_db_info", "sw4_version",
 ]
@@ -30,7 +31,7 @@ class DbInfo(ctypes.Structure):
     _fields_ = [("num_sequences", ctypes.c_uint64), ("num_residues", ctypes.c_uint64), ("min_length", ctypes.c_int32),
                 ("max_length", ctypes.c_int32), ("partition_counts", ctypes.c_uint64 * 36),
                 ("shard_rank", ctypes.c_int32), ("shard_world", ctypes.c_int32), ("shard_sequences", ctypes.c_uint64),
-                ("shard_residues", ctypes.c_uint64)]
+                ("shard_residues", ctypes.c_uint64), ("streaming", ctypes.c_int32), ("num_batches", ctypes.c_int32)]
 
 
 _lib = None
@@ -53,15 +54,19 @@ def load() -> ctypes.CDLL:
     lib.sw4_set_num_top.argtypes = [vp, ci]
     lib.sw4_set_blosum.argtypes = [vp, ci]
     lib.sw4_set_kernel_types.argtypes = [vp, ci, ci, ci, ci]
+    lib.sw4_set_mem_config.argtypes = [vp, ctypes.POINTER(MemConfig)]
     lib.sw4_set_shard.argtypes = [vp, ci, ci]
     lib.sw4_set_database_files.argtypes = [vp, ctypes.c_char_p, ci]
     lib.sw4_set_database_memory.argtypes = [vp, vp, vp, vp, vp, vp, cs]
+    lib.sw4_set_database_shard_memory.argtypes = [vp, vp, vp, vp, vp, vp, cs, vp, cs]
     lib.sw4_set_pseudo_database.argtypes = [vp, cs, ci, ci]
+    lib.sw4_set_pseudo_database_lengths.argtypes = [vp, vp, cs, ctypes.c_uint64, vp, ctypes.POINTER(vp), ctypes.c_int32]
     lib.sw4_upload_database.argtypes = [vp]
     lib.sw4_scan.argtypes = [vp, ctypes.c_char_p, ctypes.c_int32, vp, vp, ctypes.POINTER(ctypes.c_int32),
                              ctypes.POINTER(Stats)]
+    lib.sw4_scan_many.argtypes = [vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, vp, vp, vp,
+                                  ctypes.POINTER(Stats), ctypes.POINTER(Stats)]
     lib.sw4_last_scan_all_scores.argtypes = [vp, vp, vp, cs, ctypes.POINTER(cs)]
-    lib.sw4_reference_header.argtypes = [vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(cs)]
     lib.sw4_reference_header.argtypes = [vp, ctypes.c_int32, ctypes.POINTER(vp), ctypes.POINTER(cs)]
     lib.sw4_reference_length.argtypes = [vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
     lib.sw4_reference_sequence.argtypes = [vp, ctypes.c_int32, ctypes.c_char_p, cs, ctypes.POINTER(cs)]

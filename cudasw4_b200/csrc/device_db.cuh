@@ -54,25 +54,66 @@ __global__ void build_profile_kernel(const uint8_t* __restrict__ qcodes, int qle
     profile[(size_t)f * stride + p] = v;
 }
 
-// One thread per (pair-block, column). blockItem[b] names the work item (a pair of subjects) block b belongs to; the
-// block covers columns [seg*columns, (seg+1)*columns) of the pair, seg = b - item.firstBlock.
+// Work items of a single-segment length class, generated on the device: consecutive subjects [first, first+count) are
+// paired; item k = (first+2k, first+2k+1 or none) and owns pair-block k.
 struct PairItem { int subject0, subject1, firstBlock, numSegments; };  // same layout as sw4::S16Item
 
+__global__ void make_pair_items_kernel(PairItem* __restrict__ items, int numItems, int first, int count) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= numItems) return;
+    const int s0 = first + 2 * k;
+    items[k] = PairItem{s0, (2 * k + 1 < count) ? s0 + 1 : -1, k, 1};
+}
+
+// Residue codes above 20 become 20 and the padding bytes behind every sequence (up to the next multiple of 4) are set to
+// 20, whatever the caller's arrays held there. One thread per 4-byte word; `wordSubject` is not needed: the padding is
+// fixed per subject by a second launch dimension (one thread per subject).
+__global__ void sanitize_codes_kernel(uint32_t* __restrict__ words, size_t numWords) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numWords) return;
+    const uint32_t w = words[i];
+    uint32_t r = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        const uint32_t c = (w >> (8 * b)) & 0xffu;
+        r |= (c > 20u ? 20u : c) << (8 * b);
+    }
+    if (r != w) words[i] = r;
+}
+__global__ void pad_codes_kernel(uint8_t* __restrict__ chars, const size_t* __restrict__ offsets,
+                                 const int32_t* __restrict__ lengths, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const size_t end = offsets[i + 1];
+    for (size_t p = offsets[i] + (size_t)lengths[i]; p < end; p++) chars[p] = 20;
+}
+
+// One thread per (pair-block, 4 columns). blockItem[b] names the work item (a pair of subjects) block b belongs to
+// (nullptr: block b belongs to item b); the block covers columns [seg*columns, (seg+1)*columns) of the pair,
+// seg = b - item.firstBlock. `offsets` and `lengths` are indexed by the items' subject indices (the caller shifts the
+// pointers when the block of sequences at `chars` does not start at subject 0). Sequences start on 4-byte boundaries
+// and are padded with code 20 to a multiple of 4, so four columns of one subject are one aligned 32-bit load.
 __global__ void build_pair_blocks_kernel(const uint8_t* __restrict__ chars, const size_t* __restrict__ offsets,
                                          const int32_t* __restrict__ lengths, const PairItem* __restrict__ items,
                                          const int32_t* __restrict__ blockItem, int numBlocks, int columns,
                                          uint16_t* __restrict__ cols) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)numBlocks * columns;
+    const int quads = columns >> 2;
+    const long long total = (long long)numBlocks * quads;
     if (gid >= total) return;
-    const int b = (int)(gid / columns), c = (int)(gid % columns);
-    const PairItem it = items[blockItem[b]];
+    const int b = (int)(gid / quads), c = (int)(gid % quads) * 4;
+    const PairItem it = items[blockItem ? blockItem[b] : b];
     const long long col = (long long)(b - it.firstBlock) * columns + c;
-    int r0 = 20, r1 = 20;
-    if (it.subject0 >= 0 && col < lengths[it.subject0]) r0 = chars[offsets[it.subject0] + col];
-    if (it.subject1 >= 0 && col < lengths[it.subject1]) r1 = chars[offsets[it.subject1] + col];
-    r0 = min(r0, 20); r1 = min(r1, 20);
-    cols[gid] = (uint16_t)(r0 + 21 * r1);
+    uint32_t w0 = 0x14141414u, w1 = 0x14141414u;  // 20 20 20 20
+    if (it.subject0 >= 0 && col < lengths[it.subject0]) w0 = *reinterpret_cast<const uint32_t*>(chars + offsets[it.subject0] + col);
+    if (it.subject1 >= 0 && col < lengths[it.subject1]) w1 = *reinterpret_cast<const uint32_t*>(chars + offsets[it.subject1] + col);
+    uint32_t f[4];
+#pragma unroll
+    for (int x = 0; x < 4; x++) f[x] = ((w0 >> (8 * x)) & 0xffu) + 21u * ((w1 >> (8 * x)) & 0xffu);
+    uint2 out;
+    out.x = f[0] | (f[1] << 16);
+    out.y = f[2] | (f[3] << 16);
+    *reinterpret_cast<uint2*>(cols + (size_t)b * columns + c) = out;
 }
 
 }  // namespace sw4

@@ -79,6 +79,8 @@ __device__ __forceinline__ void long_ring_fill(uint32_t loBase, uint32_t hiBase,
     }
 }
 
+// (a template only so that the header can be included by several translation units)
+template <int kInstance = 0>
 __global__ void __launch_bounds__(kLongMaxWarps * 32, 1) sw_s16_long_kernel(const S16LongParams prm) {
     constexpr int R = kLongR;
     extern __shared__ __align__(16) unsigned char smem[];

@@ -41,6 +41,8 @@ struct S32Params {
     int* statCount;
 };
 
+// (a template only so that the header can be included by several translation units)
+template <int kInstance = 0>
 __global__ void __launch_bounds__(kS32Threads) sw_s32_kernel(const S32Params prm) {
     constexpr int R = kS32R;
     __shared__ int Msm[21 * 21];

@@ -18,12 +18,12 @@ _FREQ = np.array([8.25, 5.53, 4.06, 5.45, 1.37, 3.93, 6.75, 7.07, 2.27, 5.96, 9.
 _FREQ = _FREQ / _FREQ.sum()
 _CDF = np.cumsum(_FREQ)
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
 def load_queries() -> list[tuple[str, str]]:
     """The 20 benchmark queries of the reference (allqueries.fasta), carried as a fixture (header, letters)."""
-    with open(os.path.join(_GOLDEN, "allqueries.json")) as f:
+    with open(os.path.join(_DATA, "allqueries.json")) as f:
         return [(r["header"], r["sequence"]) for r in json.load(f)["records"]]
 
 
@@ -74,6 +74,31 @@ def pseudo_subject(length: int, seed: int = 42) -> np.ndarray:
         out[k] = int(prod) >> 32
         k += 1
     return out
+
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+_PSEUDO_CUM = np.array([21, 35, 46, 60, 63, 73, 91, 109, 115, 130, 155, 170, 176, 186, 198, 214, 228, 231, 238, 256])
+_PSEUDO_TABLE = np.searchsorted(_PSEUDO_CUM, np.arange(256), side="right").astype(np.uint8)
+
+
+def _mix64(z: np.ndarray) -> np.ndarray:
+    """splitmix64 finaliser on uint64 arrays (wrap-around arithmetic), as sw4_mix64 in csrc/engine.cu."""
+    with np.errstate(over="ignore"):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def pseudo_lengths_sequence(seed: int, gid: int, length: int) -> np.ndarray:
+    """Residue codes of sequence `gid` of sw4_set_pseudo_database_lengths(seed): the checker-side restatement of the
+    generator in cudasw4_b200/csrc/engine.cu."""
+    key = _mix64(np.array([(seed + gid) & 0xFFFFFFFFFFFFFFFF], dtype=np.uint64))[0]
+    words = (length + 7) // 8
+    with np.errstate(over="ignore"):
+        w = _mix64(key + np.arange(words, dtype=np.uint64))
+    b = (w[:, None] >> (np.arange(8, dtype=np.uint64) * np.uint64(8))[None, :]) & np.uint64(0xFF)
+    return _PSEUDO_TABLE[b.reshape(-1)[:length].astype(np.int64)]
 
 
 def config_c1(seed: int = 1, n: int = 10_000):

@@ -6,7 +6,8 @@
 //
 // Differences, all deliberate:
 //   * setGapOpenScore/setGapExtendScore work (the shipped align never calls them; our CLI does).
-//   * the database is always fully resident on the GPUs (the reference's streaming mode loses scores).
+//   * a database that fits MemoryConfig::maxGpuMem is resident on the GPUs (--uploadFull); a larger one is streamed in
+//     batches on every scan with all scores kept (the reference's streaming mode loses scores).
 //   * result order is (score desc, id asc) for any database size / GPU count (the reference's order above 1e6
 //     subjects is a thrust artefact); length-0 subjects score 0 instead of -1.
 #ifndef CUDASW4_B200_FACADE_CUH
@@ -116,7 +117,10 @@ public:
         check(sw4_set_kernel_types(handle, (int)val.singlePassType, (int)val.manyPassType_small, (int)val.manyPassType_large,
                                    (int)val.overflowType));
     }
-    void setMemoryConfig(const MemoryConfig&) {}                                                      // :609 (fixed at construction)
+    void setMemoryConfig(const MemoryConfig& val) {                                                   // :609-611
+        sw4_mem_config mem{val.maxBatchBytes, val.maxBatchSequences, val.maxTempBytes, val.maxGpuMem};
+        check(sw4_set_mem_config(handle, &mem));
+    }
 
     std::string_view getReferenceHeader(ReferenceIdT referenceId) const {                             // :613
         const char* p = nullptr; size_t n = 0;
@@ -144,6 +148,30 @@ public:
         result.referenceIds.assign(ids.begin(), ids.begin() + count);
         result.stats.numOverflows = st.num_overflows; result.stats.seconds = st.seconds; result.stats.gcups = st.gcups;
         return result;
+    }
+
+    // Extension (no reference counterpart: its align scans one query at a time, src/main.cu:228-255):
+    // all queries with several scans in flight per GPU. Results equal one scan() per query, in query order.
+    std::vector<ScanResult> scanMany(const std::vector<std::string_view>& queries, BenchmarkStats* total = nullptr) {
+        sw4_db_info info{};
+        check(sw4_get_db_info(handle, &info));
+        const size_t nq = queries.size();
+        const size_t stride = (size_t)std::max(numTop, 0);
+        std::vector<const char*> ptrs(nq);
+        std::vector<int32_t> lens(nq), counts(nq, 0);
+        for (size_t i = 0; i < nq; i++) { ptrs[i] = queries[i].data(); lens[i] = (int32_t)queries[i].size(); }
+        std::vector<int32_t> scores(std::max<size_t>(1, nq * stride)), ids(std::max<size_t>(1, nq * stride));
+        std::vector<sw4_stats> per(std::max<size_t>(1, nq));
+        sw4_stats tot{};
+        check(sw4_scan_many(handle, ptrs.data(), lens.data(), (int32_t)nq, scores.data(), ids.data(), counts.data(), per.data(), &tot));
+        std::vector<ScanResult> out(nq);
+        for (size_t i = 0; i < nq; i++) {
+            out[i].scores.assign(scores.begin() + i * stride, scores.begin() + i * stride + counts[i]);
+            out[i].referenceIds.assign(ids.begin() + i * stride, ids.begin() + i * stride + counts[i]);
+            out[i].stats = BenchmarkStats{per[i].num_overflows, per[i].seconds, per[i].gcups};
+        }
+        if (total) *total = BenchmarkStats{tot.num_overflows, tot.seconds, tot.gcups};
+        return out;
     }
 
     void printDBInfo() const {                                                                        // :799-807

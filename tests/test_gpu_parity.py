@@ -380,3 +380,207 @@ def test_full_size_peak_config_properties():
             assert int(scores.astype(np.int64).sum()) == 1_000_000 * kat[qi]
             assert res.scores == [kat[qi]] * 10 and res.referenceIds == list(range(10))
             assert res.stats.numOverflows == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: multi-shard on one GPU, query batching, streaming mode, pre-sharded databases, device top-k of any length,
+# and the BASELINE configurations C3 / C5 at (or near) their specified shapes
+# ---------------------------------------------------------------------------------------------------------------------
+def _check_all(eng, oracle, db, q, blosum, gop, gex, k, res=None):
+    res = res or eng.scan(dbformat.decode(q))
+    scores, ids = eng.lastScanAllScores()
+    assert sorted(ids.tolist()) == list(range(db.num_sequences))
+    ref = oracle.scan(blosum, q, db, gop, gex)
+    got = np.empty(db.num_sequences, np.int32)
+    got[ids] = scores
+    bad = np.nonzero(got != ref)[0]
+    assert len(bad) == 0, (len(q), bad[:8], got[bad[:8]], ref[bad[:8]], db.lengths[bad[:8]])
+    s, i = oracle.topk(ref, k)
+    assert res.scores == s.tolist() and res.referenceIds == i.tolist()
+    return ref
+
+
+def test_multi_shard_handle_on_one_gpu(oracle):
+    """The in-process multi-GPU driver (one host thread per shard, host merge of the per-shard top-k lists; the
+    analogue of src/cudasw4.cuh:1490-2262, 1415-1458) exercised on a single GPU: the same device id three times."""
+    db, rng = _mixed_db(31, 6000, 10, 1400, [2500, 5000])
+    qs = [synth.random_residues(rng, n) for n in (200, 431)]
+    with sw.CudaSW4(deviceIds=[0, 0, 0], numTop=20, blosumType=62) as eng:
+        eng.setDatabase(db)
+        assert eng.dbInfo().shard_sequences == db.num_sequences
+        for q in qs:
+            _check_all(eng, oracle, db, q, 62, -11, -1, 20)
+        res, total = eng.scanMany([dbformat.decode(q) for q in qs])
+        for q, r in zip(qs, res):
+            s, i = oracle.topk(oracle.scan(62, q, db, -11, -1), 20)
+            assert r.scores == s.tolist() and r.referenceIds == i.tolist()
+
+
+def test_scan_many_equals_single_scans(oracle):
+    """sw4_scan_many: several queries in flight; results must equal one scan per query."""
+    db, rng = _mixed_db(41, 5000, 5, 1200, [1500, 2600, 4000])
+    lens = (1, 17, 144, 333, 600, 97, 1500, 256, 40)
+    qs = [synth.random_residues(rng, n) for n in lens]
+    qs[6][200:200 + 1200] = db.sequence(db.num_sequences - 3)[:1200]  # a strong hit on a long subject
+    with _engine(numTop=12, blosumType=62) as eng:
+        eng.setDatabase(db)
+        singles = [eng.scan(dbformat.decode(q)) for q in qs]
+        many, total = eng.scanMany([dbformat.decode(q) for q in qs])
+        assert len(many) == len(qs)
+        for q, a, b in zip(qs, singles, many):
+            assert a.scores == b.scores and a.referenceIds == b.referenceIds
+            assert a.stats.numOverflows == b.stats.numOverflows and b.stats.cells == a.stats.cells
+            s, i = oracle.topk(oracle.scan(62, q, db, -11, -1), 12)
+            assert b.scores == s.tolist() and b.referenceIds == i.tolist()
+        assert total.cells == sum(r.stats.cells for r in many) and total.gcups > 0
+        # the context of the last query holds its scores
+        _check_all(eng, oracle, db, qs[-1], 62, -11, -1, 12, res=many[-1])
+        assert eng.scanMany([])[0] == []
+
+
+def test_streaming_mode_equals_resident(oracle):
+    """a database larger than maxGpuMem is streamed in batches on every scan (two device slots, upload of
+    the next batch overlapping the kernels); scores, top-k and overflow statistics must equal the resident run."""
+    rng = np.random.default_rng(61)
+    q = synth.random_residues(rng, 5600)
+    q[::4] = 17
+    L = np.concatenate([rng.integers(1, 1300, 30000), rng.integers(1300, 9000, 300)])
+    seqs = [synth.random_residues(rng, int(n)) for n in L]
+    seqs += [synth.mutate(rng, q, 0.03) for _ in range(12)] + [np.concatenate([synth.random_residues(rng, 2000), q, synth.random_residues(rng, 900)])]
+    db = dbformat.from_sequences(seqs)
+    qs = [q, synth.random_residues(rng, 150), synth.random_residues(rng, 700)]
+    with _engine(numTop=15, blosumType=62) as eng:
+        eng.setDatabase(db)
+        resident = [eng.scan(dbformat.decode(x)) for x in qs]
+        assert eng.dbInfo().streaming == 0 and eng.dbInfo().num_batches == 1
+        refs = [oracle.scan(62, x, db, -11, -1) for x in qs]
+        for x, r, ref in zip(qs, resident, refs):
+            s, i = oracle.topk(ref, 15)
+            assert r.scores == s.tolist() and r.referenceIds == i.tolist()
+        assert resident[0].stats.numOverflows >= 12
+    for max_mem in (24 << 20, 14 << 20):
+        mc = sw.MemoryConfig(maxGpuMem=max_mem)
+        with _engine(numTop=15, blosumType=62, memoryConfig=mc) as eng:
+            eng.setDatabase(db)
+            for rep in range(2):
+                for x, r, ref in zip(qs, resident, refs):
+                    res = eng.scan(dbformat.decode(x))
+                    assert res.scores == r.scores and res.referenceIds == r.referenceIds
+                    assert res.stats.numOverflows == r.stats.numOverflows
+                    scores, ids = eng.lastScanAllScores()
+                    got = np.empty(db.num_sequences, np.int32)
+                    got[ids] = scores
+                    assert (got == ref).all(), np.nonzero(got != ref)[0][:10]
+            info = eng.dbInfo()
+            assert info.streaming == 1 and info.num_batches >= 3, (info.streaming, info.num_batches)
+            many, _ = eng.scanMany([dbformat.decode(x) for x in qs] * 2)  # one pass over the batches serves all six
+            for r, m in zip(resident * 2, many):
+                assert m.scores == r.scores and m.referenceIds == r.referenceIds and m.stats.numOverflows == r.stats.numOverflows
+            # switching the memory configuration re-plans the layout
+            eng.setMemoryConfig(sw.MemoryConfig())
+            res = eng.scan(dbformat.decode(qs[1]))
+            assert res.scores == resident[1].scores and eng.dbInfo().streaming == 0
+
+
+def test_streaming_multi_shard(oracle):
+    db, rng = _mixed_db(67, 20000, 8, 900, [1800, 3000])
+    q = synth.random_residues(rng, 280)
+    with sw.CudaSW4(deviceIds=[0, 0], numTop=10, blosumType=62, memoryConfig=sw.MemoryConfig(maxGpuMem=3 << 20)) as eng:
+        eng.setDatabase(db)
+        _check_all(eng, oracle, db, q, 62, -11, -1, 10)
+        assert eng.dbInfo().streaming == 1 and eng.dbInfo().num_batches >= 2
+
+
+def test_presharded_database(oracle):
+    """Every rank holds only its own shard in host memory (sw4_set_database_shard_memory): global ids in the results,
+    merged lists equal the oracle's over the whole database."""
+    db, rng = _mixed_db(83, 5000, 10, 1300, [2200])
+    q = synth.random_residues(rng, 310)
+    ref = oracle.scan(62, q, db, -11, -1)
+    world = 3
+    merged, seen = [], np.zeros(db.num_sequences, bool)
+    for rank in range(world):
+        gids = np.array([i for i in range(db.num_sequences) if (i // 256) % world == rank], dtype=np.int32)
+        local = dbformat.from_sequences([db.sequence(int(i)) for i in gids])
+        with _engine(numTop=15, blosumType=62) as eng:
+            eng.setDatabaseShard(local, gids, db.num_sequences)
+            res = eng.scan(dbformat.decode(q))
+            scores, ids = eng.lastScanAllScores()
+            assert ids.tolist() == gids.tolist() and (scores == ref[gids]).all()
+            seen[ids] = True
+            merged += list(zip(res.scores, res.referenceIds))
+            assert eng.getReferenceLength(int(gids[5])) == int(db.lengths[gids[5]])
+            assert eng.dbInfo().num_sequences == db.num_sequences and eng.dbInfo().shard_sequences == len(gids)
+    assert seen.all()
+    merged.sort(key=lambda t: (-t[0], t[1]))
+    s, i = oracle.topk(ref, 15)
+    assert [m[0] for m in merged[:15]] == s.tolist() and [m[1] for m in merged[:15]] == i.tolist()
+
+
+def test_device_top_k_of_any_length():
+    """k above the shared-memory path (4096) is selected and sorted on the device too (the reference accepts any --top,
+    src/cudasw4.cuh:1365-1401); heavy ties must come out in ascending id order."""
+    queries = synth.load_queries()
+    with _engine(numTop=6000, blosumType=62) as eng:
+        eng.setPseudoDatabase(20001, 128)
+        res = eng.scan(queries[3][1])
+        assert res.scores == [29] * 6000 and res.referenceIds == list(range(6000))
+        eng.setNumTop(20001)
+        res = eng.scan(queries[3][1])
+        assert res.scores == [29] * 20001 and res.referenceIds == list(range(20001))
+    with sw.CudaSW4(deviceIds=[0, 0], numTop=9000, blosumType=62) as eng:
+        eng.setPseudoDatabase(20001, 128)
+        res = eng.scan(queries[3][1])
+        assert res.scores == [29] * 9000 and res.referenceIds == list(range(9000))
+
+
+def test_gap_setters_keep_the_other_score(oracle):
+    db, rng = _mixed_db(97, 400, 30, 400)
+    q = synth.random_residues(rng, 200)
+    with _engine(numTop=5, blosumType=45, gop=-13, gex=-2) as eng:
+        eng.setDatabase(db)
+        eng.setGapOpenScore(-10)   # must keep gex = -2
+        _check_all(eng, oracle, db, q, 45, -10, -2, 5)
+        eng.setGapExtendScore(-3)  # must keep gop = -10
+        _check_all(eng, oracle, db, q, 45, -10, -3, 5)
+        with pytest.raises(sw.SW4Error):
+            eng.setGapOpenScore(-100000)
+        _check_all(eng, oracle, db, q, 45, -10, -3, 5)  # a rejected value changes nothing
+
+
+def test_c3_shaped_sample(oracle):
+    """BASELINE configs[2] (Swiss-Prot-shaped) as a 50,000-subject sample of the same length law incl. subjects above
+    8000 residues and planted homologs: every score, top-10 and overflow count vs the oracle for a short and a long query."""
+    rng = np.random.default_rng(3)
+    L = synth.lognormal_lengths(rng, 50_000, 5.683, 0.636, 2, 35213)
+    L = np.concatenate([L, rng.integers(8001, 20000, 6)])
+    queries = [dbformat.encode(q) for _, q in synth.load_queries()]
+    planted = [queries[0].copy(), synth.mutate(rng, queries[0], 0.1, 0), queries[12].copy(), synth.mutate(rng, queries[12], 0.1, 0)]
+    L[: len(planted)] = [len(p) for p in planted]
+    db = synth._db_from_sorted_lengths(rng, L, planted)
+    with _engine(numTop=10, blosumType=62) as eng:
+        eng.setDatabase(db)
+        for qi in (0, 12):
+            res = eng.scan(dbformat.decode(queries[qi]))
+            ref = _check_all(eng, oracle, db, queries[qi], 62, -11, -1, 10, res=res)
+            Ls = db.lengths
+            assert res.stats.numOverflows == int(((ref >= 25000) & (Ls > 240) & (Ls <= 8000)).sum())
+            assert res.scores[0] == int(oracle.scan(62, queries[qi], dbformat.from_sequences([queries[qi]]), -11, -1)[0])
+
+
+@pytest.mark.parametrize("blosum,gop,gex", [(45, -9, -3), (80, -14, -2)])
+def test_c5_at_spec_long_query_custom_gaps(oracle, blosum, gop, gex):
+    """BASELINE configs[4] at its largest shape: a 35,000-residue query against 20-35 k subjects with planted copies
+    (exact, 10 % mutated, embedded in flanks), custom gap scores on the saturating path: scores far above 32767."""
+    rng = np.random.default_rng(5)
+    q = synth.random_residues(rng, 35000)
+    seqs = [synth.random_residues(rng, int(n)) for n in (20000, 23500, 27111, 31000, 35000)]
+    fl, fr = 211, 97
+    seqs += [q.copy(), synth.mutate(rng, q, 0.10, indels=2), np.concatenate([synth.random_residues(rng, fl), q[:30000], synth.random_residues(rng, fr)])]
+    seqs += [synth.random_residues(rng, int(n)) for n in (300, 1024, 1025, 5000)]
+    db = dbformat.from_sequences(seqs)
+    with _engine(numTop=6, blosumType=blosum) as eng:
+        eng.setGapScores(gop, gex)
+        eng.setDatabase(db)
+        ref = _check_all(eng, oracle, db, q, blosum, gop, gex, 6)
+        assert int(ref.max()) > 100000 and int((ref > 32767).sum()) >= 3

@@ -33,7 +33,7 @@ def main():
     os.makedirs(G, exist_ok=True)
     recs = dbformat.read_fasta(os.path.join(REF, "allqueries.fasta"))
     assert len(recs) == 20 and sum(len(s) for _, s in recs) == 41752
-    with open(os.path.join(G, "allqueries.json"), "w") as f:
+    with open(os.path.join(ROOT, "cudasw4_b200", "data", "allqueries.json"), "w") as f:
         json.dump({"source": "reference allqueries.fasta (20 UniProt proteins used by run*benchmark.sh)",
                    "records": [{"header": hd, "sequence": s} for hd, s in recs]}, f, indent=0)
 
