@@ -197,6 +197,141 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+C4_QUERIES = (0, 5, 9, 14, 19)
+C4_SUBJECTS = 65_000_000
+C4_RESIDUES = 17.0e9
+C4_SEED = 4
+
+
+def c4_leg(rank, local_rank, world, dev):
+    """STRONG scaling on one fixed UniRef50-shaped database (see the module docstring). Returns the `c4` object on rank 0."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import cudasw4_b200 as sw
+    from cudasw4_b200 import dbformat, synth
+    from cudasw4_b200.distributed import gather_topk
+    from tests import oracle_lib  # the checker (CPU oracle); never on the measured path
+
+    n_seqs = int(os.environ.get("SW4_BENCH_C4_SUBJECTS", C4_SUBJECTS))
+    t0 = time.perf_counter()
+    lengths = synth.config_c4_lengths(seed=C4_SEED, n=n_seqs, total=C4_RESIDUES * n_seqs / C4_SUBJECTS).astype(np.int32)
+    queries = synth.load_queries()
+    planted = {}
+    for qi in C4_QUERIES:  # one exact copy of each query in the slot of a subject of the same length
+        codes = dbformat.encode(queries[qi][1])
+        gid = int(np.searchsorted(lengths, len(codes), side="left"))
+        while gid in planted:
+            gid += 1
+        if gid < n_seqs and int(lengths[gid]) == len(codes):
+            planted[gid] = codes
+    eng = sw.CudaSW4(deviceIds=[local_rank], numTop=TOP_K, blosumType=62)
+    eng.setShard(rank, world)
+    eng.setPseudoDatabaseLengths(lengths, C4_SEED, planted)
+    gen_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    eng.prefetchDBToGpus()
+    upload_s = time.perf_counter() - t0
+    info = eng.dbInfo()
+    total_residues = float(lengths.astype(np.int64).sum())
+    oracle = oracle_lib.load()
+    planted_by_len = {len(c): g for g, c in planted.items()}
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    per_query, checked, sample_total, sum_cells, sum_s = [], True, 0, 0.0, 0.0
+    for qi in C4_QUERIES:
+        q = queries[qi][1]
+        qc = dbformat.encode(q)
+        sync()
+        res = eng.scan(q)
+        t = torch.tensor([res.stats.seconds], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        seconds = float(t.item())
+        merged = gather_topk(res.scores, res.referenceIds, TOP_K, device=dev)
+        # checks: (1) the planted copy is the best hit with the query's self score; (2) a sample of this rank's scores
+        # (evenly spaced over its shard + its longest subjects) equals the CPU oracle on re-generated sequences
+        ok = True
+        if len(qc) in planted_by_len:
+            self_score = int(oracle.scan(62, qc, dbformat.from_sequences([qc]), -11, -1)[0])
+            ok &= merged[0] == (self_score, planted_by_len[len(qc)])
+        scores, ids = eng.lastScanAllScores()
+        n_local = len(ids)
+        want = max(64, 3040 // world)
+        pos = np.unique(np.concatenate([np.arange(0, n_local, max(1, n_local // want)), np.arange(max(0, n_local - 8), n_local)]))
+        seqs = [planted[int(g)] if int(g) in planted else synth.pseudo_lengths_sequence(C4_SEED, int(g), int(lengths[g])) for g in ids[pos]]
+        sample = dbformat.from_sequences(seqs, presorted=True)
+        ok &= bool((oracle.scan(62, qc, sample, -11, -1, threads=host_threads()) == scores[pos]).all())
+        flag = torch.tensor([1 if ok else 0, len(pos)], dtype=torch.int64, device=dev)
+        if world > 1:
+            both = [torch.zeros_like(flag) for _ in range(world)]
+            dist.all_gather(both, flag)
+            ok = all(int(b[0]) == 1 for b in both)
+            n_sample = sum(int(b[1]) for b in both)
+        else:
+            n_sample = len(pos)
+        checked &= ok
+        sample_total = n_sample
+        cells = total_residues * len(qc)
+        sum_cells += cells
+        sum_s += seconds
+        per_query.append({"query": qi, "length": len(qc), "gcups": cells / 1e9 / seconds, "seconds": seconds,
+                          "top1": list(merged[0]) if merged else None, "overflows": res.stats.numOverflows})
+    eng.close()
+    if rank != 0:
+        return None
+    return {"gcups": sum_cells / 1e9 / sum_s, "n_gpus": world, "scaling": "strong", "per_query": per_query, "checked": bool(checked),
+            "check": f"planted copies of queries {list(C4_QUERIES)} found with their self scores; {sample_total} sampled subjects "
+                     f"(all ranks) x 5 queries equal to the CPU oracle",
+            "database": {"subjects": n_seqs, "residues": total_residues, "max_length": int(lengths[-1]),
+                         "shard_subjects_rank0": int(info.shard_sequences), "shard_residues_rank0": int(info.shard_residues)},
+            "generate_s": gen_s, "upload_s": upload_s, "queries": list(C4_QUERIES)}
+
+
+def ref_gpu_leg(local_rank, ours_e2e_gcups, ours_value_gcups):
+    """The reference's own align binary (oracle/_ref/align: unmodified sources built for sm_100a) on the same PseudoDB,
+    same GPU, --dpx and default (half2) kernel types, as runpeakbenchmark.sh:27,44-50 runs it."""
+    import re
+    import tempfile
+    from cudasw4_b200 import dbformat, synth
+    binary = os.path.join(ROOT, "oracle", "_ref", "align")
+    if not os.path.exists(binary):
+        return {"unavailable": "oracle/_ref/align not built (needs /root/reference at build time)"}
+    env = dict(os.environ)
+    visible = env.get("CUDA_VISIBLE_DEVICES")
+    env["CUDA_VISIBLE_DEVICES"] = visible.split(",")[local_rank] if visible else str(local_rank)
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        qfile = os.path.join(tmp, "allqueries.fasta")
+        dbformat.write_fasta(qfile, synth.load_queries())
+        for tag, extra in (("dpx", ["--dpx"]), ("half2", [])):
+            args = [binary, "--query", qfile, "--pseudodb", str(N_SUBJECTS), str(SUBJECT_LEN), "--top", "0", "--verbose",
+                    "--uploadFull", "--prefetchDBFile", "--mat", "blosum62"] + extra
+            try:
+                r = subprocess.run(args, cwd=tmp, env=env, capture_output=True, text=True, timeout=300)
+            except subprocess.TimeoutExpired:
+                out[tag + "_gcups"] = None
+                continue
+            tot = re.findall(r"Total time: ([0-9.e+-]+) s, ([0-9.e+-]+) GCUPS", r.stdout)
+            per = re.findall(r"Scan time: ([0-9.e+-]+) s, ([0-9.e+-]+) GCUPS", r.stdout)
+            out[tag + "_gcups"] = float(tot[-1][1]) if tot else None
+            if per:  # aggregate of its per-query device-timed scans: sum(cells) / sum(scan seconds)
+                secs = sum(float(p[0]) for p in per)
+                out[tag + "_scan_gcups"] = N_SUBJECTS * SUBJECT_LEN * sum(len(q) for _, q in synth.load_queries()) / 1e9 / secs if secs > 0 else None
+            if r.returncode != 0:
+                out[tag + "_error"] = (r.stderr or r.stdout)[-200:]
+    best = max([v for v in (out.get("dpx_gcups"), out.get("half2_gcups")) if v] or [0.0])
+    best_scan = max([v for v in (out.get("dpx_scan_gcups"), out.get("half2_scan_gcups")) if v] or [0.0])
+    out["ratio_vs_best"] = ours_e2e_gcups / best if best else None           # our end-to-end vs its "Total time" GCUPS
+    out["ratio_vs_best_scan"] = ours_value_gcups / best_scan if best_scan else None  # device-timed scans on both sides
+    out["command"] = "align --query allqueries.fasta --pseudodb 1000000 256 --top 0 --verbose --uploadFull --prefetchDBFile --mat blosum62 [--dpx]"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -204,6 +339,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 strong-scaling leg")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own GPU binary")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -213,6 +350,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # one hardware queue per length-class stream
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -228,7 +366,8 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     queries = synth.load_queries()
-    total_q = sum(len(q) for _, q in queries)
+    letters = [q for _, q in queries]
+    total_q = sum(len(q) for q in letters)
     eng = sw.CudaSW4(deviceIds=[local_rank], numTop=TOP_K, blosumType=62)  # raises if libsw4b200.so / the GPU is missing
     eng.setShard(rank, world)
     eng.setPseudoDatabase(N_SUBJECTS * world, SUBJECT_LEN, 42)
@@ -239,6 +378,7 @@ def main():
     shard_residues = int(info.shard_residues)
 
     from cudasw4_b200.distributed import gather_topk
+    single = bool(os.environ.get("SW4_BENCH_SINGLE"))  # development switch: one sw4_scan per query instead of sw4_scan_many
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -247,18 +387,31 @@ def main():
         torch.cuda.synchronize(dev)
 
     def one_step():
-        """20 scans; returns (device seconds, kernel seconds, launches, merged top-k of the last query)."""
-        dev_s = ker_s = 0.0
-        launches = 0
+        """One pass of the hot path over the query batch: the 20 queries through sw4_scan_many (host letters in, top-k
+        out). Returns (device-timed seconds of the call, launches, merged top-k of the last query)."""
+        if single:
+            dev_s, launches, results = 0.0, 0, []
+            for q in letters:
+                r = eng.scan(q)
+                dev_s += r.stats.seconds
+                launches += r.stats.kernelLaunches
+                results.append(r)
+        else:
+            results, total = eng.scanMany(letters)
+            dev_s, launches = total.seconds, total.kernelLaunches
+        # the only exchange step: k (score, id) pairs per rank and query (NCCL all_gather), merged on every rank
         merged = None
-        for _, q in queries:
-            res = eng.scan(q)
-            dev_s += res.stats.seconds
-            ker_s += res.stats.kernelSeconds
-            launches += res.stats.kernelLaunches
-            # the only exchange step: k (score, id) pairs per rank (one NCCL all_gather of 80 bytes), merged on every rank
-            merged = gather_topk(res.scores, res.referenceIds, TOP_K, device=dev)
-        return dev_s, ker_s, launches, merged
+        for r in results:
+            merged = gather_topk(r.scores, r.referenceIds, TOP_K, device=dev)
+        return dev_s, launches, merged
+
+    def kernel_step():
+        """Same 20 queries one sw4_scan at a time: the score kernels of one query run alone, so their CUDA-event time
+        (stats.kernel_seconds) is exclusive. Used for the roofline only."""
+        ker_s = 0.0
+        for q in letters:
+            ker_s += eng.scan(q).stats.kernelSeconds
+        return ker_s
 
     for _ in range(args.warmup):
         one_step()
@@ -266,29 +419,39 @@ def main():
     sampler.start()
     barrier()
     wall0 = time.perf_counter()
-    dev_s = ker_s = 0.0
+    dev_s = 0.0
     launches = 0
     merged = None
     for _ in range(args.steps):
-        d, k, l, merged = one_step()
+        d, l, merged = one_step()
         dev_s += d
-        ker_s += k
         launches += l
     barrier()
     wall = time.perf_counter() - wall0
+    ker_s = 0.0
+    for _ in range(args.steps):
+        ker_s += kernel_step()
     clocks = sampler.stop()
+    eng.close()
 
-    # max over ranks
+    # max over ranks; exact cell count = sum of the ranks' shard residues
     t = torch.tensor([dev_s, ker_s, wall], dtype=torch.float64, device=dev)
-    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    lt = torch.tensor([launches, shard_residues], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
     dev_s, ker_s, wall = [float(x) for x in t.cpu()]
-    launches = int(lt.item())
+    launches, all_residues = int(lt[0].item()), int(lt[1].item())
+
+    c4 = None
+    if not args.no_c4 and os.environ.get("SW4_BENCH_C4", "1") != "0":
+        try:
+            c4 = c4_leg(rank, local_rank, world, dev)
+        except Exception as exc:  # the headline line must still be printed
+            c4 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank == 0:
-        cells_per_step = float(shard_residues) * total_q * world
+        cells_per_step = float(all_residues) * total_q
         cells = cells_per_step * args.steps
         value = cells / 1e9 / dev_s
         e2e = cells / 1e9 / wall
@@ -300,13 +463,17 @@ def main():
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         peak_gcups = sms * 4 * 64 / 7.0 * sm_hz / 1e9 * world
         # HBM side (for the record): per scan the kernel streams the shard once, 1 byte per residue (u16 fused pair code)
-        hbm_bytes = float(shard_residues) * len(queries) * args.steps * world
+        hbm_bytes = float(all_residues) * len(queries) * args.steps
         line = {
             "metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "s16x2 (DPX) with exact s32 re-scoring", "data": "synthetic",
             "config": {"workload": CONFIG_NAME, "subjects_per_gpu": N_SUBJECTS, "subject_length": SUBJECT_LEN,
                        "queries": len(queries), "query_residues": total_q, "cells_per_step": cells_per_step,
+                       "api": "20 sw4_scan calls per step" if single else "one sw4_scan_many call per step (20 queries, 3 in flight)",
+                       "timing": "value: CUDA events inside libsw4b200.so on its own streams, first query's upload -> last "
+                                 "result in pinned host memory, max over ranks; e2e: host wall clock around the same calls + "
+                                 "the NCCL gather of the per-rank top-k",
                        "l2_note": "each scan streams 256 MB of database per GPU (> 126 MB L2) and scans alternate 20 different "
                                   "query profiles, so no timed iteration re-reads L2-resident inputs",
                        "db_upload_s": upload_s, "top1": merged[0] if merged else None},
@@ -318,17 +485,26 @@ def main():
                          "frac": kernel_gcups / peak_gcups,
                          "peak_model": f"{sms} SMs x 4 schedulers x 64 cells / 7 clk (3.5 DPX ALU-pipe ops per s16x2 cell-pair at "
                                        f"1 warp-inst / 2 clk, measured) x {sm_hz/1e6:.0f} MHz (nvidia-smi under load)",
+                         "measured": "score kernels alone (CUDA events around them on the library's stream), the 20 queries "
+                                     "scanned one at a time so that the intervals do not overlap, same number of steps",
                          "traffic": (_traffic() or {}).get("dram_bytes_read_plus_write_per_launch"),
                          "traffic_detail": _traffic(),
                          "hbm": {"achieved": hbm_bytes / 1e9 / ker_s, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                  "frac": hbm_bytes / 1e9 / ker_s / peaks.get("hbm_gbs", 6650.0), "peak_source": peak_src,
                                  "note": "database streaming only; the path is compute bound (1/len_query bytes per cell)"}},
         }
+        if c4 is not None:
+            line["c4"] = c4
+        if world == 1 and not args.no_ref_gpu:
+            try:
+                line["ref_gpu"] = ref_gpu_leg(local_rank, e2e, value)
+            except Exception as exc:
+                line["ref_gpu"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"], _, _ = cpu_baseline()
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -21,6 +21,7 @@ struct Options {
     bool help = false, uploadFull = false, pseudo = false, printPartitions = false, interactive = false, verbose = false,
          prefetchFile = false;
     int top = 10, gop = -11, gex = -1, pseudoLen = 0;
+    int batchQueries = 1;  // extension: queries handed to one scanMany call (1 = one scan per query, as the reference)
     size_t pseudoNum = 0;
     cudasw4::BlosumType blosum = cudasw4::BlosumType::BLOSUM62_20;
     cudasw4::KernelTypeConfig kernels;
@@ -63,6 +64,7 @@ bool parseArgs(int argc, char** argv, Options& o) {
         else if (a == "--uploadFull") o.uploadFull = true;
         else if (a == "--verbose") o.verbose = true;
         else if (a == "--interactive") o.interactive = true;
+        else if (a == "--batchQueries" && i + 1 < argc) o.batchQueries = std::max(1, std::atoi(argv[++i]));
         else if (a == "--printLengthPartitions") o.printPartitions = true;
         else if (a == "--prefetchDBFile") o.prefetchFile = true;
         else if (a == "--top") o.top = std::atoi(need(i).c_str());
@@ -121,6 +123,7 @@ void printHelp(const char* prog) {
               << "   --of file : Result output file. Default /dev/stdout\n"
               << "   --tsv : tab-separated output\n"
               << "   --verbose, --printLengthPartitions, --interactive, --help\n"
+              << "   --batchQueries n : (extension) scan n queries of a file with several scans in flight per GPU; same results\n"
               << "   --prefetchDBFile, --uploadFull, --pseudodb num length\n"
               << "   --singlePassType, --manyPassType_small, --manyPassType_large, --overflowType : Half2, DPXs16, DPXs32, Float\n";
 }
@@ -167,11 +170,30 @@ void printTSV(std::ostream& os, const cudasw4::ScanResult& r, const cudasw4::Cud
     }
 }
 
+void reportQuery(const Options& o, cudasw4::CudaSW4& sw, std::ostream& out, int64_t qnum, const std::string& header,
+                 const std::string& sequence, const cudasw4::ScanResult& r);
+
 void processQuery(const Options& o, cudasw4::CudaSW4& sw, std::ostream& out, int64_t qnum, const std::string& header,
                   const std::string& sequence) {
     std::cout << "Processing query " << qnum << " ... ";
     std::cout.flush();
     cudasw4::ScanResult r = sw.scan(sequence.data(), (int)sequence.size());
+    reportQuery(o, sw, out, qnum, header, sequence, r);
+}
+
+// --batchQueries: the queries go through one scanMany call; output is written in query order exactly as above
+void processQueryBatch(const Options& o, cudasw4::CudaSW4& sw, std::ostream& out, int64_t firstQnum,
+                       const std::vector<std::string>& headers, const std::vector<std::string>& sequences) {
+    std::vector<std::string_view> views(sequences.begin(), sequences.end());
+    const std::vector<cudasw4::ScanResult> results = sw.scanMany(views);
+    for (size_t i = 0; i < results.size(); i++) {
+        std::cout << "Processing query " << firstQnum + (int64_t)i << " ... ";
+        reportQuery(o, sw, out, firstQnum + (int64_t)i, headers[i], sequences[i], results[i]);
+    }
+}
+
+void reportQuery(const Options& o, cudasw4::CudaSW4& sw, std::ostream& out, int64_t qnum, const std::string& header,
+                 const std::string& sequence, const cudasw4::ScanResult& r) {
     if (o.verbose) std::cout << "Done. Scan time: " << r.stats.seconds << " s, " << r.stats.gcups << " GCUPS\n";
     else std::cout << "Done.\n";
     if (o.top > 0) {
@@ -219,9 +241,24 @@ int main(int argc, char** argv) {
                 sw4::SequenceFileReader reader(qf);
                 int64_t qnum = 0;
                 sw.totalTimerStart();
-                while (reader.next()) {
-                    processQuery(o, sw, out, qnum, reader.getCurrentHeader(), reader.getCurrentSequence());
-                    qnum++;
+                if (o.batchQueries <= 1) {
+                    while (reader.next()) {
+                        processQuery(o, sw, out, qnum, reader.getCurrentHeader(), reader.getCurrentSequence());
+                        qnum++;
+                    }
+                } else {
+                    std::vector<std::string> headers, sequences;
+                    bool more = true;
+                    while (more) {
+                        headers.clear();
+                        sequences.clear();
+                        while ((int)sequences.size() < o.batchQueries && (more = reader.next())) {
+                            headers.push_back(reader.getCurrentHeader());
+                            sequences.push_back(reader.getCurrentSequence());
+                        }
+                        if (!sequences.empty()) processQueryBatch(o, sw, out, qnum, headers, sequences);
+                        qnum += (int64_t)sequences.size();
+                    }
                 }
                 const auto total = sw.totalTimerStop();
                 if (o.verbose) std::cout << "Total time: " << total.seconds << " s, " << total.gcups << " GCUPS\n";

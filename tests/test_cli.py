@@ -89,3 +89,22 @@ def test_align_plain_output_and_pseudodb(tmp_path):
     if os.path.exists(REF_ALIGN):
         _run_align(REF_ALIGN, ["--query", "q.fa", "--pseudodb", "5000", "256", "--top", "3", "--dpx", "--uploadFull", "--of", "ref.txt"], str(tmp_path))
         assert open(tmp_path / "ref.txt").read() == open(tmp_path / "res.txt").read()
+
+
+@pytest.mark.gpu
+def test_align_batch_queries_and_streaming_write_the_same_file(tmp_path):
+    """--batchQueries (several scans in flight, sw4_scan_many) and --maxGpuMem small enough to stream the database in
+    batches must produce byte-identical result files to the plain one-query-at-a-time resident run."""
+    _build_cli()
+    recs, queries = synth.config_c1(seed=2, n=12000)
+    dbformat.write_fasta(str(tmp_path / "db.fa"), recs)
+    dbformat.write_fasta(str(tmp_path / "q.fa"), queries[:9])
+    subprocess.run([MAKEDB, str(tmp_path / "db.fa"), str(tmp_path / "db")], check=True, stdout=subprocess.DEVNULL)
+    common = ["--query", "q.fa", "--db", "db", "--top", "12", "--mat", "blosum62", "--dpx"]
+    _run_align(ALIGN, common + ["--of", "plain.txt"], str(tmp_path))
+    _run_align(ALIGN, common + ["--of", "batched.txt", "--batchQueries", "4"], str(tmp_path))
+    _run_align(ALIGN, common + ["--of", "streamed.txt", "--maxGpuMem", "5M", "--batchQueries", "16", "--verbose"], str(tmp_path))
+    plain = open(tmp_path / "plain.txt").read()
+    assert plain.count("Query ") == 9
+    assert open(tmp_path / "batched.txt").read() == plain
+    assert open(tmp_path / "streamed.txt").read() == plain

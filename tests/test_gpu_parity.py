@@ -584,3 +584,33 @@ def test_c5_at_spec_long_query_custom_gaps(oracle, blosum, gop, gex):
         eng.setDatabase(db)
         ref = _check_all(eng, oracle, db, q, blosum, gop, gex, 6)
         assert int(ref.max()) > 100000 and int((ref > 32767).sum()) >= 3
+
+
+def test_pseudo_database_with_lengths_is_reproducible(oracle):
+    """sw4_set_pseudo_database_lengths: every rank generates its own shard of the same database; the checker-side
+    restatement (synth.pseudo_lengths_sequence) re-creates any sequence; planted sequences replace their slot."""
+    rng = np.random.default_rng(4)
+    lengths = np.sort(synth.lognormal_lengths(rng, 3000, 5.247, 0.80, 11, 45000)).astype(np.int32)
+    q = synth.random_residues(rng, 180)
+    gid = int(np.searchsorted(lengths, 180))
+    lengths[gid] = 180
+    lengths = np.sort(lengths)
+    gid = int(np.searchsorted(lengths, 180))
+    seqs = [synth.pseudo_lengths_sequence(77, g, int(lengths[g])) for g in range(len(lengths))]
+    seqs[gid] = q
+    db = dbformat.from_sequences(seqs, presorted=True)
+    ref = oracle.scan(62, q, db, -11, -1)
+    merged = []
+    for rank in range(2):
+        with _engine(numTop=10, blosumType=62) as eng:
+            eng.setShard(rank, 2)
+            eng.setPseudoDatabaseLengths(lengths, 77, {gid: q})
+            res = eng.scan(dbformat.decode(q))
+            scores, ids = eng.lastScanAllScores()
+            assert ((ids // 256) % 2 == rank).all() and (scores == ref[ids]).all()
+            assert eng.getReferenceSequence(int(ids[7])) == dbformat.decode(seqs[int(ids[7])])
+            merged += list(zip(res.scores, res.referenceIds))
+    merged.sort(key=lambda t: (-t[0], t[1]))
+    s, i = oracle.topk(ref, 10)
+    assert [m[0] for m in merged[:10]] == s.tolist() and [m[1] for m in merged[:10]] == i.tolist()
+    assert merged[0][1] == gid
