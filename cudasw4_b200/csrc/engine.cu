@@ -242,8 +242,15 @@ struct Ctx {
     DevBuf<uint8_t> dQueryCodes;
     DevBuf<uint32_t> dProfile;
     DevBuf<int8_t> dMatrix;
-    DevBuf<uint2> dBorder;          // border rows of the long-subject kernels: [borderRowArrays][borderStride]
+    // Border rows of the long-subject kernels: row arrays of borderStride (H, E) pairs. The first borderSlots * 32 arrays
+    // belong to the multi-segment two-row kernels (several length classes run concurrently: a CTA takes a free slot of 32
+    // arrays, dBorderSlots holds the flags); the remaining borderRowArrays arrays (from borderB on) serve the kernels that
+    // run one at a time per scan (array kernels, one-warp-per-pair kernels, exact 32-bit kernels).
+    DevBuf<uint2> dBorder;
+    DevBuf<int> dBorderSlots;
+    uint2* borderB = nullptr;
     size_t borderRowArrays = 0, borderStride = 0;
+    int borderSlots = 0;
     DevBuf<unsigned long long> dClassNs;
     DevBuf<TopkCand> dCand;
     DevBuf<int32_t> dTopScores, dTopIds;
@@ -341,10 +348,11 @@ struct Shard {
 // steps (row pairs) between two alignments of a group: ceil(q/2) + G - 1 rounded up to a batch, at least 16 so that
 // no lane of a half-warp starts before step 0
 // The 256-column class can run as 16 lanes x 16 columns or as 8 lanes x 32 columns on the same pair-blocks (a block is
-// 256 consecutive column codes either way). 8 x 32 has 8 fewer fill steps per alignment, 16 x 16 the better steady state
-// (fewer live registers): short queries take the former (measured cross-over between q = 1000 and 1500).
+// 256 consecutive column codes either way). 8 x 32 has 8 fewer fill steps per alignment and half the per-pair hand-over
+// work; with the gap scores as immediates it is the faster shape at every query length (1 M x 256: 8.04 vs 7.59 TCUPS),
+// so it is the default. SW4_CLASS256_CROSSOVER=q sends queries of q residues and more to 16 x 16 (round 1: 1200).
 static inline LengthClass shapeForQuery(const LengthClass& lc, int qlen) {
-    static const int crossover = [] { const char* e = getenv("SW4_CLASS256_CROSSOVER"); return e ? atoi(e) : 1200; }();
+    static const int crossover = [] { const char* e = getenv("SW4_CLASS256_CROSSOVER"); return e ? atoi(e) : 0x7fffffff; }();
     if (lc.capacity == 256 && !lc.wide && qlen < crossover) return LengthClass{3, 32, 256, false, false};
     return lc;
 }
@@ -367,6 +375,11 @@ struct Engine {
     bool useLongKernel = [] { const char* e = getenv("SW4_NO_LONG_KERNEL"); return !e; }();
     int longMinWarps = [] { const char* e = getenv("SW4_LONG_MIN_WARPS"); return e ? std::max(2, atoi(e)) : 2; }();
     int backfillItems = [] { const char* e = getenv("SW4_BACKFILL_ITEMS"); return e ? std::max(1, atoi(e)) : 4; }();
+    // classes above 512 columns: the multi-segment two-rows-per-step kernel (default) or the older full-warp one-row kernel
+    bool twoRowMulti = [] { const char* e = getenv("SW4_NO_TWO_ROW_MULTI"); return !e; }();
+    // the long class goes to the CTA-wide array kernel when it has fewer items than this per group of the GPU (latency
+    // bound: few very long alignments), else to the multi-segment kernel (throughput bound)
+    double longArrayMaxItemsPerGroup = [] { const char* e = getenv("SW4_LONG_ARRAY_ITEMS_PER_GROUP"); return e ? atof(e) : 3.0; }();
     int pipelineDepth = [] { const char* e = getenv("SW4_PIPELINE"); return e ? std::min(kMaxContexts, std::max(1, atoi(e))) : 3; }();
     int shardRank = 0, shardWorld = 1;
     std::unique_ptr<HostDB> db;
@@ -702,10 +715,11 @@ struct Engine {
         if (fresh) {  // untimed warm-up scan: loads every kernel this database will launch and sizes the scratch buffers
             std::string warm;
             for (int i = 0; i < 320; i++) warm.push_back("ARNDCQEGHILKMFPSTWYV"[(i * 7) % 20]);
-            QueryRef q{warm.data(), (int)warm.size()};
+            // (as many copies as queries can be in flight, so that every context exists before the first timed scan)
+            std::vector<QueryRef> q((size_t)pipelineDepth, QueryRef{warm.data(), (int)warm.size()});
             const int k = (int)std::min<size_t>((size_t)std::max(numTop, 1), std::min<size_t>(std::max<size_t>(db->nGlobal, 1), 16));
             std::vector<std::vector<ShardResult>> res;
-            runAllShards(&q, 1, k, res);
+            runAllShards(q.data(), (int)q.size(), k, res);
         }
     }
 
@@ -746,16 +760,24 @@ struct Engine {
             // border rows of the long-subject kernels: one row array per warp (one-warp-per-pair kernels) or per CTA (array
             // kernels); the kernels of one scan that use them run one after the other, so they share one buffer. Its
             // size is bounded by max_temp_bytes: fewer row arrays = fewer CTAs on those kernels.
-            ctx.borderStride = (size_t)(cap + 31) / 32 * 32 + 32;
+            // (one row array = cap + 128 (H, E) pairs; the two-row multi-segment kernel keeps one per GROUP, two per warp, as
+            // cap / 2 + 64 entries of both rows of a step)
+            ctx.borderStride = (size_t)(cap + 31) / 32 * 32 + 128;
             const bool needBorder = sh.maxLen > 512;
-            size_t rows = needBorder ? (size_t)sh.smCount * kS16Warps : (size_t)kS16Warps;
+            const size_t groupsPerCta = (size_t)kS16Warps * 2;
+            size_t rows = needBorder ? (size_t)sh.smCount * (groupsPerCta + kS16Warps) : (size_t)kS16Warps;
             const size_t maxRows = mem.max_temp_bytes / (ctx.borderStride * sizeof(uint2));
             if (maxRows < (size_t)kS16Warps)
                 fail(SW4_ERR_NOMEM, "max_temp_bytes (%zu MiB) cannot hold the border rows of a %d-residue query (%zu MiB needed at least)",
                      mem.max_temp_bytes >> 20, qlen, (kS16Warps * ctx.borderStride * sizeof(uint2)) >> 20);
             rows = std::min(rows, maxRows / kS16Warps * kS16Warps);
-            ctx.borderRowArrays = rows;
+            // two thirds for the slots of the multi-segment kernels (none when the budget is that small: those classes
+            // then fall back to the one-warp-per-pair kernel)
+            ctx.borderSlots = needBorder ? (int)std::min<size_t>((size_t)sh.smCount, rows * 2 / 3 / groupsPerCta) : 0;
+            ctx.borderRowArrays = rows - (size_t)ctx.borderSlots * groupsPerCta;
             ctx.dBorder.ensure(rows * ctx.borderStride);
+            ctx.borderB = ctx.dBorder.p + (size_t)ctx.borderSlots * groupsPerCta * ctx.borderStride;
+            ctx.dBorderSlots.ensure((size_t)std::max(ctx.borderSlots, 1));
         }
     }
 
@@ -778,6 +800,7 @@ struct Engine {
         if (qlen) SW4_CUDA(cudaMemcpyAsync(ctx.dQueryLetters.p, ctx.hQuery.p, (size_t)qlen, cudaMemcpyHostToDevice, st));
         SW4_CUDA(cudaMemcpyAsync(ctx.dMatrix.p, matrix, 441, cudaMemcpyHostToDevice, st));
         SW4_CUDA(cudaMemsetAsync(ctx.dCounters.p, 0, kNumCounters * sizeof(int), st));
+        if (ctx.borderSlots) SW4_CUDA(cudaMemsetAsync(ctx.dBorderSlots.p, 0, (size_t)ctx.borderSlots * sizeof(int), st));
         // every scan starts from "-1 = not scored" so that a subject the kernels missed can never keep an old score;
         // empty subjects (and everything, for an empty query) score 0 by definition
         SW4_CUDA(cudaMemsetAsync(ctx.dScores.p, qlen == 0 ? 0 : 0xff, std::max<size_t>(sh.n, 1) * sizeof(int32_t), st));
@@ -854,55 +877,78 @@ struct Engine {
                     prm.elapsedNs = ctx.dClassNs.p;
                     prm.activeGroups = activeGroups;
                 };
-                // the multi-segment class runs on the CTA-wide array kernel whenever the query is long enough to keep
-                // at least two warps of an array busy (kernels_s16_long.cuh)
+                // the long class runs on the CTA-wide array kernel when the query is long enough to keep at least two warps of
+                // an array busy (kernels_s16_long.cuh) AND the class is too small to fill the GPU's groups a few times over
+                int longWarps = 0;
+                const int p0 = (qlen + 32 + 15) / 16 * 16;
                 if (lc.multi && useLongKernel) {
-                    const int p0 = (qlen + 32 + 15) / 16 * 16;
-                    int longWarps = kLongMaxWarps;
+                    longWarps = kLongMaxWarps;
                     while (longWarps > 1 && kLongLag * longWarps + 64 > p0) longWarps >>= 1;
-                    if (longWarps >= longMinWarps) {
-                        S16LongParams lp{};
-                        lp.cols = cols;
-                        lp.items = items;
-                        lp.lengths = sh.dLengths.p;
-                        lp.numItems = cl.numItems;
-                        lp.ticket = ctx.dCounters.p + 8 + cl.cls;
-                        lp.warps = longWarps;
-                        lp.ringSlots = s16_long_ring_slots(longWarps);
-                        lp.profLo = ctx.dProfile.p + (size_t)kFused * profStride;
-                        lp.profHi = ctx.dProfile.p + (size_t)(kFused + 21) * profStride;
-                        lp.profStride = profStride;
-                        lp.qlen = qlen;
-                        lp.period = p0;
-                        lp.gop2 = gop2;
-                        lp.gex2 = gex2;
-                        lp.ovfThreshold = kS16OverflowThreshold;
-                        lp.statThreshold = statThreshold();
-                        lp.scores = ctx.dScores.p;
-                        lp.ovfList = ctx.dOvfList.p;
-                        lp.ovfCount = ctx.dCounters.p + 0;
-                        lp.statCount = ctx.dCounters.p + 1;
-                        lp.elapsedNs = ctx.dClassNs.p;
-                        lp.border = ctx.dBorder.p;
-                        lp.borderStride = (int)ctx.borderStride;
-                        const int smemBytes = s16_long_smem_bytes(longWarps);
-                        const int ctasPerSm = std::max(1, std::min(kLongMaxWarps / longWarps, (227 * 1024) / (smemBytes + 1024)));
-                        int g = std::max(1, std::min(cl.numItems, std::min(sh.smCount * ctasPerSm, sh.smCount * 8)));
-                        g = (int)std::min<size_t>((size_t)g, ctx.borderRowArrays);
-                        SW4_CUDA(launch_s16_long(lp, g, cst));
-                        ctx.launches++;
-                        SW4_CUDA(cudaEventRecord(ctx.evJoin[ci % kMaxClassStreams], cst));
-                        SW4_CUDA(cudaStreamWaitEvent(st, ctx.evJoin[ci % kMaxClassStreams], 0));
-                        continue;
-                    }
+                    if (longWarps < longMinWarps) longWarps = 0;
+                    if (longWarps && twoRowMulti && cl.numItems > longArrayMaxItemsPerGroup * sh.smCount * kS16Warps * 2) longWarps = 0;
                 }
+                if (longWarps) {
+                    S16LongParams lp{};
+                    lp.cols = cols;
+                    lp.items = items;
+                    lp.lengths = sh.dLengths.p;
+                    lp.numItems = cl.numItems;
+                    lp.ticket = ctx.dCounters.p + 8 + cl.cls;
+                    lp.warps = longWarps;
+                    lp.ringSlots = s16_long_ring_slots(longWarps);
+                    lp.profLo = ctx.dProfile.p + (size_t)kFused * profStride;
+                    lp.profHi = ctx.dProfile.p + (size_t)(kFused + 21) * profStride;
+                    lp.profStride = profStride;
+                    lp.qlen = qlen;
+                    lp.period = p0;
+                    lp.gop2 = gop2;
+                    lp.gex2 = gex2;
+                    lp.ovfThreshold = kS16OverflowThreshold;
+                    lp.statThreshold = statThreshold();
+                    lp.scores = ctx.dScores.p;
+                    lp.ovfList = ctx.dOvfList.p;
+                    lp.ovfCount = ctx.dCounters.p + 0;
+                    lp.statCount = ctx.dCounters.p + 1;
+                    lp.elapsedNs = ctx.dClassNs.p;
+                    lp.border = ctx.borderB;
+                    lp.borderStride = (int)ctx.borderStride;
+                    const int smemBytes = s16_long_smem_bytes(longWarps);
+                    const int ctasPerSm = std::max(1, std::min(kLongMaxWarps / longWarps, (227 * 1024) / (smemBytes + 1024)));
+                    int g = std::max(1, std::min(cl.numItems, std::min(sh.smCount * ctasPerSm, sh.smCount * 8)));
+                    g = (int)std::min<size_t>((size_t)g, ctx.borderRowArrays);
+                    SW4_CUDA(launch_s16_long(lp, g, cst));
+                    ctx.launches++;
+                    SW4_CUDA(cudaEventRecord(ctx.evJoin[ci % kMaxClassStreams], cst));
+                    SW4_CUDA(cudaStreamWaitEvent(st, ctx.evJoin[ci % kMaxClassStreams], 0));
+                    continue;
+                }
+                // classes above 512 columns (576..1024 and the long class): the two-rows-per-step kernel over 16 x R-column
+                // segments, the border column handed from segment to segment (kernels_s16.cuh, MULTI)
+                const bool segmented = lc.wide && twoRowMulti && ctx.borderSlots > 0;
                 S16Params narrow{};
                 S16WideParams wide{};
-                if (lc.wide) {
+                if (segmented) {
+                    const int groupsPerCta2 = kS16Warps * 2;
+                    grid = (cl.numItems + groupsPerCta2 * backfillItems - 1) / (groupsPerCta2 * backfillItems);
+                    grid = std::max(1, std::min(width, grid));
+                    if (grid > 1) grid = (grid + 1) & ~1;
+                    grid = std::max(1, std::min(grid, width));
+                    fillCommon(narrow);
+                    narrow.logG = 4;
+                    narrow.activeGroups = std::min(groupsPerCta2, std::max(1, (cl.numItems + grid - 1) / grid));
+                    narrow.period = std::max(32, s16Period(qlen, 16));
+                    narrow.statThreshold = statThreshold();
+                    narrow.lengths = sh.dLengths.p;
+                    narrow.border = reinterpret_cast<uint4*>(ctx.dBorder.p);
+                    narrow.borderStride = (int)(ctx.borderStride / 2);
+                    narrow.borderSlots = ctx.dBorderSlots.p;
+                    narrow.numBorderSlots = ctx.borderSlots;
+                    narrow.blockScale = 2;
+                } else if (lc.wide) {
                     fillCommon(wide);
                     wide.period = s16WidePeriod(qlen, G);
                     wide.lengths = sh.dLengths.p;
-                    wide.border = ctx.dBorder.p;
+                    wide.border = ctx.borderB;
                     wide.borderStride = (int)ctx.borderStride;
                 } else {
                     fillCommon(narrow);
@@ -910,7 +956,8 @@ struct Engine {
                 }
                 auto launchClass = [&](int g, cudaStream_t strm, int ctaOffset) {
                     cudaError_t e;
-                    if (lc.wide) { wide.ctaOffset = ctaOffset; e = launch_s16_wide(lc.R, lc.multi, wide, g, strm); }
+                    if (segmented) { narrow.ctaOffset = ctaOffset; e = launch_s16_multi(lc.R, narrow, g, strm); }
+                    else if (lc.wide) { wide.ctaOffset = ctaOffset; e = launch_s16_wide(lc.R, lc.multi, wide, g, strm); }
                     else { narrow.ctaOffset = ctaOffset; e = launch_s16(lc.R, narrow, g, strm); }
                     if (e == cudaErrorInvalidValue) { cudaGetLastError(); fail(SW4_ERR_INVALID, "no kernel for class G=%d R=%d", G, lc.R); }
                     SW4_CUDA(e);
@@ -943,7 +990,7 @@ struct Engine {
                 lp.prof = reinterpret_cast<const int32_t*>(ctx.dProfile.p + (size_t)(kFused + 42) * profStride);
                 lp.profStride = profStride; lp.qlen = qlen; lp.period = p0; lp.gop = gop; lp.gex = gex;
                 lp.scores = ctx.dScores.p;
-                lp.border = reinterpret_cast<int2*>(ctx.dBorder.p);
+                lp.border = reinterpret_cast<int2*>(ctx.borderB);
                 lp.borderStride = (int)ctx.borderStride;
                 SW4_CUDA(launch_s32_long(lp, (int)std::min<size_t>((size_t)sh.smCount, ctx.borderRowArrays), st));
             } else {
@@ -951,7 +998,7 @@ struct Engine {
                 p.chars = arena; p.offsets = offsetsBySubject; p.lengths = sh.dLengths.p;
                 p.list = ctx.dOvfList.p; p.listCountPtr = ctx.dCounters.p + 0; p.listCountHost = 0;
                 p.query = ctx.dQueryCodes.p; p.qlen = qlen; p.matrix = ctx.dMatrix.p; p.gop = gop; p.gex = gex;
-                p.border = reinterpret_cast<int2*>(ctx.dBorder.p); p.borderStride = (int)ctx.borderStride;
+                p.border = reinterpret_cast<int2*>(ctx.borderB); p.borderStride = (int)ctx.borderStride;
                 p.ticket = ctx.dCounters.p + 3; p.scores = ctx.dScores.p;
                 p.statThreshold = 0x7fffffff;
                 p.statCount = ctx.dCounters.p + 1;

@@ -13,7 +13,7 @@
 //    (G = 8 or 16 lanes); a group aligns one *pair-block* (two subjects, G*R columns, R register columns per lane) and
 //    restarts on its own schedule every P steps (P = ceil(q/2)+G-1 rounded to 8): no warp-wide fill/drain.
 //    Row pairs in [q, 2P) are *gap rows*: computed like any other row (no branch, hence no register shuffling at a merge
-//    point) on profile entries of -16000 with the hand-over inputs forced to the boundary values.
+//    point) on profile entries of -16000. Whatever they leave in a lane's registers is reset at the group's restart.
 //  * Substitution scores come from a *positional* query profile prof[f][row] = (M[q_row][s1] << 16 | M[q_row][s0]) for
 //    the fused residue pair f = s0 + 21*s1. A 64-row sliding window lives in shared memory as ring[f][96] (64 slots +
 //    32 mirrored), refilled 16 rows ahead with cp.async. Lane l reads rows 2(t-l), 2(t-l)+1: the 16 lanes of a
@@ -22,8 +22,12 @@
 //    batch are unrolled and the column addresses advance by 64 bytes once per batch. No per-cell address arithmetic.
 //  * The device database stores pair-blocks as fused u16 column codes (device_db.cuh), fetched one alignment ahead with
 //    cp.async into a per-group staging area; work items are handed out through an atomic ticket.
-//  * Subjects longer than 512 run on the full-warp, one-row-per-step variant (kernels_s16_wide.cuh): a 32-lane group
-//    at two rows per lane would need a 128-row ring, which does not fit next to the staging area.
+//  * Subjects longer than 16 x R columns (MULTI instantiations): a group aligns the 16 x R-column segments of a pair one
+//    after the other, one period each. The last column's (H, E) of both rows of every step goes to a per-group border
+//    array in global memory (one 16-byte store per step by the group's last lane) and comes back as the left border of
+//    the next segment through a small double-buffered staging area in shared memory (cp.async one batch ahead, one
+//    128-bit shared load per step); F never crosses a segment (it runs along the query), the running maximum carries
+//    over. (kernels_s16_wide.cuh holds the older full-warp one-row-per-step form of the same idea.)
 //
 // Arithmetic (bit-exact vs the oracle): H = max(0, diag+s, E, F); t = H+gop; E' = max(E+gex, t); F' = max(F+gex, t);
 // packed modular s16 adds, -16000 as minus infinity; the running maximum is taken over diag+s (equal to max H: a best
@@ -37,7 +41,10 @@
 
 namespace sw4 {
 
-constexpr int kS16Threads = 512;           // 16 warps, one CTA per SM
+#ifndef SW4_S16_THREADS
+#define SW4_S16_THREADS 512                // development switch (kernel-variant sweeps)
+#endif
+constexpr int kS16Threads = SW4_S16_THREADS;  // 16 warps, one CTA per SM
 constexpr int kS16Warps = kS16Threads / 32;
 constexpr int kRingSlots = 64;             // query rows held in the ring
 constexpr int kRingStride = 96;            // words per fused-pair row: 32 mirrored + 64 live slots
@@ -77,6 +84,13 @@ struct S16Params {
     int activeGroups;            // groups per CTA that take work (fewer than all when the class cannot fill its SMs: the
                                  // items are then spread over more SMs and every warp gets a larger share of its scheduler)
     int ctaOffset;               // index of this launch's first CTA within the class (a class may be split in two launches)
+    // MULTI instantiations only (subjects longer than one 16 x R segment):
+    const int32_t* lengths;      // [numLocalSubjects] (statistics rule; segments that are padding only are skipped)
+    uint4* border;               // [gridGroups][borderStride]: (H, E) of a segment's last column for the two rows of every step
+    int borderStride;            // entries per group, >= period + 16
+    int* borderSlots;            // [numBorderSlots] zero-initialised flags: a CTA owns the border arrays of the slot it holds
+    int numBorderSlots;          //   (several classes run concurrently on one border buffer; one CTA fits per SM)
+    int blockScale;              // the class stores blocks of blockScale * 16 * R columns (2 for the 32-lane layouts)
 };
 
 template <int N, class Fn, int... Is>
@@ -131,8 +145,11 @@ __host__ __device__ constexpr int s16_prefetch_depth() {
 #endif
 }
 
-template <int R>
-constexpr int s16_smem_bytes() { return kRingBytes + kS16Warps * 32 * R * 2 + kS16Warps * 4 * kGroupStateInts * 4; }
+constexpr int kBorderStageBytes = 2 * kBatchSteps * 16;  // per group: two batches of (H_a, E_a, H_b, E_b) per step
+template <int R, bool MULTI = false>
+constexpr int s16_smem_bytes() {
+    return kRingBytes + kS16Warps * 32 * R * 2 + kS16Warps * 4 * kGroupStateInts * 4 + (MULTI ? kS16Warps * 2 * kBorderStageBytes : 0);
+}
 
 // Refill the ring slots of query rows [x0, x0+16) (x0 % 16 == 0); p0 = x0 mod periodRows (periodRows % 16 == 0).
 __device__ __forceinline__ void ring_fill(uint32_t ringBase, const uint32_t* __restrict__ profile, int profStride, int x0,
@@ -149,8 +166,38 @@ __device__ __forceinline__ void ring_fill(uint32_t ringBase, const uint32_t* __r
     cp_async_commit();
 }
 
-// R = register columns per lane.
-template <int R>
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+template <int IMM>
+__device__ __forceinline__ uint4 lds_u128_imm(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(IMM));
+    return v;
+}
+__device__ __forceinline__ void sts_u128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Gap-score sets with their own instantiations (gop, gex replicated in both halves): 0 = run-time values,
+// 1 = -11 / -1 (BLOSUM62's default and what the reference's align always runs),
+// 2 = -13 / -2 (the documented BLOSUM45 / BLOSUM50 default), 3 = -10 / -1 (BLOSUM80).
+constexpr int kS16GapSets = 4;
+__host__ __device__ constexpr uint2 s16_gap_set(int gaps) {
+    return gaps == 1 ? uint2{0xfff5fff5u, 0xffffffffu} : gaps == 2 ? uint2{0xfff3fff3u, 0xfffefffeu}
+         : gaps == 3 ? uint2{0xfff6fff6u, 0xffffffffu} : uint2{0u, 0u};
+}
+inline int s16_gap_set_for(uint32_t gop2, uint32_t gex2) {
+    for (int g = 1; g < kS16GapSets; g++)
+        if (s16_gap_set(g).x == gop2 && s16_gap_set(g).y == gex2) return g;
+    return 0;
+}
+
+// R = register columns per lane. MULTI = items may span several 16 x R-column segments (G must be 16).
+// GAPS = gap-score set compiled into the instructions (0 = read prm.gop2 / prm.gex2).
+template <int R, bool MULTI = false, int GAPS = 0>
 __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params prm) {
     static_assert(R % 2 == 0, "a lane's staging slice (R u16 codes) must be a whole number of 4-byte words");
     extern __shared__ __align__(16) unsigned char smem[];
@@ -167,6 +214,30 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
     const unsigned groupMask = ((G == 16 ? 0xffffu : 0xffu)) << (g << logG);
     const int leader = g << logG;                      // lane index of the group's first lane
     const uint32_t NEG2 = ((uint32_t)(uint16_t)kNegS16 << 16) | (uint16_t)kNegS16;
+    // Gap scores: instruction immediates in the specialised instantiations (GAPS > 0), registers otherwise. An immediate
+    // saves one register-file read on three of the 5.5 recurrence instructions of a cell-pair, and operand delivery is
+    // what this loop is short of (measured on the 1 M x 256 benchmark: 7.18 -> 7.66 TCUPS).
+    const uint32_t SW4_GOP2 = GAPS > 0 ? s16_gap_set(GAPS).x : prm.gop2;
+    const uint32_t SW4_GEX2 = GAPS > 0 ? s16_gap_set(GAPS).y : prm.gex2;
+
+    // MULTI: the CTA takes a free slot of the border buffer (the length classes of a scan run concurrently and share it;
+    // a CTA that finds none waits for one: slot holders never wait for anything, so this cannot deadlock)
+    int borderSlot = 0;
+    if constexpr (MULTI) {
+        __shared__ int sBorderSlot;
+        if (threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            int i = (int)(smid % (unsigned)prm.numBorderSlots);
+            while (atomicCAS(prm.borderSlots + i, 0, 1) != 0) {
+                if (++i == prm.numBorderSlots) i = 0;
+                __nanosleep(200);
+            }
+            sBorderSlot = i;
+        }
+        __syncthreads();
+        borderSlot = sBorderSlot;
+    }
 
     // Warps that will never get work (the class was spread over more SMs than it can fill, prm.activeGroups) only keep
     // the CTA's ring going: same barriers and their share of every refill, none of the arithmetic, so the busy warps get
@@ -194,6 +265,19 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
     volatile int* gs = reinterpret_cast<volatile int*>(smem + kRingBytes + kS16Warps * 32 * R * 2) +
                        (warp * 4 + g) * kGroupStateInts;
 
+    // MULTI: border rows of this group in global memory (entry e <-> leader step e - 16, so that the last lane, which
+    // trails the leader by 15 steps, never indexes below the array) and its staging area in shared memory
+    uint4* borderBase = nullptr;
+    uint32_t bstage = 0;
+    if constexpr (MULTI) {
+        const size_t groupGlobal = (size_t)borderSlot * (kS16Warps * 2) + warp * 2 + g;
+        borderBase = prm.border + groupGlobal * (size_t)prm.borderStride + 16;
+        bstage = ringBase + kRingBytes + kS16Warps * 32 * R * 2 + kS16Warps * 4 * kGroupStateInts * 4 + (warp * 2 + g) * kBorderStageBytes;
+    }
+    bool useBorder = false;       // MULTI: the segment being computed continues an item (its left border is in `border`)
+    bool nextUseBorder = false;   // MULTI: the same for the look-ahead segment
+    int pl = 0;                   // MULTI: the group leader's step p at the start of the current batch
+
     uint32_t colAddr[R];  // ring byte address of this column's fused-pair row (lane and batch-phase offsets folded in)
     uint32_t Hp[R];       // H of the lower row (b) of the previous step
     uint32_t F[R];        // F for the upper row (a) of the next step
@@ -205,6 +289,9 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
     // step pRestart. Restarts can only fall on the first step of a batch (P and the group offsets are multiples of 8).
     int p = (hl == 0) ? 0 : P - hl;
     const int pRestart = (m == 0) ? 0 : P - m;
+#ifdef SW4_HANDOVER_IMAD
+    const uint32_t notFirst = (m != 0) ? 1u : 0u, negIfFirst = (m != 0) ? 0u : NEG2;
+#endif
     bool haveWork = false;    // a segment is being computed
     bool alive = (warp * groupsPerWarp + g) < prm.activeGroups;  // the group still has something to compute or start
 
@@ -218,9 +305,10 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
         } else {
             if (m == 0) item = atomicAdd(prm.ticket, 1);
             item = __shfl_sync(groupMask, item, leader);
-            if (item < prm.numItems) { blk = prm.items[item].firstBlock; isNew = 1; }
+            if (item < prm.numItems) { blk = prm.items[item].firstBlock * (MULTI ? prm.blockScale : 1); isNew = 1; }
         }
         if (m == 0) { gs[3] = blk >= 0; gs[4] = blk; gs[5] = isNew; gs[6] = item; }
+        if constexpr (MULTI) nextUseBorder = blk >= 0 && !isNew;
         if (blk >= 0) {
             const unsigned char* src = (const unsigned char*)(prm.cols + (size_t)blk * (G * R)) + m * (R * 2);
             if constexpr ((R * 2) % 16 == 0) {
@@ -245,6 +333,10 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
     ring_fill(ringBase, prm.profile, prm.profStride, 0, 0);
     fetch_lookahead(false, 0);
     int pfill = kBatchRows % periodRows;  // (first row of the next fill) mod periodRows
+    if constexpr (MULTI) {  // both staging buffers start out as the boundary column (H = 0, E = -inf)
+        if (m < kBatchSteps) { sts_u128(bstage + m * 16, 0, NEG2, 0, NEG2); sts_u128(bstage + 128 + m * 16, 0, NEG2, 0, NEG2); }
+    }
+    bool writeBorder = false;  // MULTI: another segment of the item follows, so the last lane stores its column
 
     uint32_t phaseBase = ringBase + (32 - 2 * hl) * 4;  // + 64 bytes (16 rows) per batch, wrapping every 4 batches
 #pragma unroll 1
@@ -270,12 +362,12 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
                     const int s0 = gs[0], s1 = gs[1];
                     const int lo = (int)(short)(r & 0xffff), hi = (int)(short)(r >> 16);
                     if (s0 >= 0) {
-                        if (lo >= prm.statThreshold) atomicAdd(prm.statCount, 1);
+                        if (lo >= prm.statThreshold && (!MULTI || prm.lengths[s0] <= kStatMaxLength)) atomicAdd(prm.statCount, 1);
                         if (lo >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = s0;
                         prm.scores[s0] = lo;
                     }
                     if (s1 >= 0) {
-                        if (hi >= prm.statThreshold) atomicAdd(prm.statCount, 1);
+                        if (hi >= prm.statThreshold && (!MULTI || prm.lengths[s1] <= kStatMaxLength)) atomicAdd(prm.statCount, 1);
                         if (hi >= prm.ovfThreshold) prm.ovfList[atomicAdd(prm.ovfCount, 1)] = s1;
                         prm.scores[s1] = hi;
                     }
@@ -286,18 +378,28 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
             const bool laNew = gs[5] != 0;
             haveWork = laValid;
             alive = laValid;
+            if constexpr (MULTI) writeBorder = false;
             if (laValid) {
                 if (laNew) {
                     const S16Item it = prm.items[gs[6]];
+                    int nseg = it.numSegments;
+                    if constexpr (MULTI) {
+                        nseg *= prm.blockScale;
+                        if (prm.blockScale > 1) {  // trailing segments that hold padding only are not computed
+                            const int len0 = prm.lengths[it.subject0], len1 = it.subject1 >= 0 ? prm.lengths[it.subject1] : 0;
+                            nseg = max(1, min(nseg, (max(len0, len1) + G * R - 1) / (G * R)));
+                        }
+                    }
                     __syncwarp(groupMask);
-                    if (m == 0) { gs[0] = it.subject0; gs[1] = it.subject1; gs[2] = it.numSegments - 1; }
-                    segsLeft = it.numSegments - 1;
+                    if (m == 0) { gs[0] = it.subject0; gs[1] = it.subject1; gs[2] = nseg - 1; }
+                    segsLeft = nseg - 1;
                     mx = 0;
-                } else {  // (items of this kernel have one segment; kept for symmetry with the wide variant)
+                } else {  // the next segment of the same item (MULTI only)
                     __syncwarp(groupMask);
                     if (m == 0) gs[2] = segsLeft - 1;
                     segsLeft -= 1;
                 }
+                if constexpr (MULTI) { useBorder = !laNew; writeBorder = segsLeft > 0; }
                 cp_async_wait_all();
                 __syncwarp(groupMask);
 #pragma unroll
@@ -308,10 +410,32 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
                 }
 #pragma unroll
                 for (int j = 0; j < R; j++) { Hp[j] = 0; F[j] = NEG2; }
-                HinPrevB = 0;
+                // the hand-over registers start from the boundary values too: between its restart and its first real row a
+                // lane runs up to G-1 gap rows whose inputs then come from reset registers of its left neighbour (which
+                // is in the same state), so nothing of the previous alignment can leak into the new one and the steps need
+                // no "is this a real row" test
+                HinPrevB = 0; HlastA = 0; ElastA = NEG2; ElastB = NEG2;
                 __syncwarp(groupMask);
                 fetch_lookahead(segsLeft > 0, laBlk);
             }
+        }
+        uint32_t bstageRd = 0;
+        uint4* borderWr = nullptr;
+        bool wb15 = false;
+        if constexpr (MULTI) {
+            // left border of the NEXT batch's steps -> the other staging buffer (cp.async, or the boundary column when that
+            // batch belongs to the first segment of an item); the next batch starts a new segment when the leader wraps
+            const int plNext = (pl + kBatchSteps >= P) ? 0 : pl + kBatchSteps;
+            const bool ub = (plNext == 0) ? nextUseBorder : useBorder;
+            if (m < kBatchSteps) {
+                const uint32_t dst = bstage + ((batch + 1) & 1) * (kBatchSteps * 16) + m * 16;
+                if (ub) cp_async16(dst, borderBase + plNext + m);
+                else sts_u128(dst, 0, NEG2, 0, NEG2);
+            }
+            cp_async_commit();
+            bstageRd = bstage + (batch & 1) * (kBatchSteps * 16);
+            borderWr = borderBase + (pl - (G - 1));  // the last lane trails the leader by G - 1 steps
+            wb15 = writeBorder && m == G - 1;
         }
         static_for<kBatchSteps>([&](auto stepIndex) {
             constexpr int i = decltype(stepIndex)::value;
@@ -320,10 +444,18 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
             uint32_t EinA = __shfl_up_sync(0xffffffffu, ElastA, 1);
             uint32_t HinB = __shfl_up_sync(0xffffffffu, Hp[R - 1], 1);
             uint32_t EinB = __shfl_up_sync(0xffffffffu, ElastB, 1);
-            const bool realA = (unsigned)(2 * p) < (unsigned)prm.qlen;
-            const bool realB = (unsigned)(2 * p + 1) < (unsigned)prm.qlen;
-            if (m == 0 || !realA) { HinA = 0; EinA = NEG2; }
-            if (m == 0 || !realB) { HinB = 0; EinB = NEG2; }
+            // the first lane of a group takes the boundary column (H = 0, E = -inf) instead of its neighbour's values
+#ifdef SW4_HANDOVER_IMAD
+            HinA *= notFirst; HinB *= notFirst;                          // IMAD: FMA pipe instead of an ALU-pipe SEL
+            EinA = EinA * notFirst + negIfFirst; EinB = EinB * notFirst + negIfFirst;
+#else
+            if constexpr (MULTI) {
+                const uint4 bv = lds_u128_imm<i * 16>(bstageRd);  // left border of this step's two rows (group broadcast)
+                if (m == 0) { HinA = bv.x; EinA = bv.y; HinB = bv.z; EinB = bv.w; }
+            } else {
+                if (m == 0) { HinA = 0; EinA = NEG2; HinB = 0; EinB = NEG2; }
+            }
+#endif
             {
                 uint32_t E1 = EinA, E2 = EinB;
                 // substitution words are fetched kPrefetch columns ahead of their use: an explicit software pipeline, because
@@ -344,15 +476,15 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
                     uint32_t na = 0, nb = 0;
                     if (j + 1 < R) na = __vadd2(Hp[j], sn.x);
                     ha = __vimax3_s16x2_relu(da, E1, F[j]);
-                    const uint32_t ta = __vadd2(ha, prm.gop2);
-                    E1 = __viaddmax_s16x2(E1, prm.gex2, ta);
-                    const uint32_t Fa = __viaddmax_s16x2(F[j], prm.gex2, ta);
+                    const uint32_t ta = __vadd2(ha, SW4_GOP2);
+                    E1 = __viaddmax_s16x2(E1, SW4_GEX2, ta);
+                    const uint32_t Fa = __viaddmax_s16x2(F[j], SW4_GEX2, ta);
                     if (j + 1 < R) nb = __vadd2(ha, sn.y);
                     const uint32_t hb = __vimax3_s16x2_relu(db, E2, Fa);
                     Hp[j] = hb;
-                    const uint32_t tb = __vadd2(hb, prm.gop2);
-                    E2 = __viaddmax_s16x2(E2, prm.gex2, tb);
-                    F[j] = __viaddmax_s16x2(Fa, prm.gex2, tb);
+                    const uint32_t tb = __vadd2(hb, SW4_GOP2);
+                    E2 = __viaddmax_s16x2(E2, SW4_GEX2, tb);
+                    F[j] = __viaddmax_s16x2(Fa, SW4_GEX2, tb);
                     mx = __vimax3_s16x2(mx, da, db);
                     da = na;
                     db = nb;
@@ -362,8 +494,13 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
                 ElastB = E2;
                 HinPrevB = HinB;
             }
-            if (++p == P) p = 0;
+            if constexpr (MULTI) {
+                if (wb15) borderWr[i] = make_uint4(HlastA, ElastA, Hp[R - 1], ElastB);  // right border of this step's two rows
+            }
         });
+        p += kBatchSteps;  // P and the lanes' offsets to their group leader are multiples of the batch
+        if (p >= P) p -= P;
+        if constexpr (MULTI) pl = (pl + kBatchSteps >= P) ? 0 : pl + kBatchSteps;
     }
     if (threadIdx.x == 0) {
         unsigned long long tEnd;
@@ -371,6 +508,10 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
         atomicMax(prm.elapsedNs, tEnd - tStart);
         atomicMax(prm.elapsedNs + 32, ~tStart);  // earliest CTA start (as a max of the complement)
         atomicMax(prm.elapsedNs + 64, tEnd);     // latest CTA end
+        if constexpr (MULTI) {  // every warp is past the last barrier: nobody touches the border arrays any more
+            __threadfence();
+            atomicExch(prm.borderSlots + borderSlot, 0);
+        }
     }
 }
 

@@ -79,8 +79,8 @@ __device__ __forceinline__ void long_ring_fill(uint32_t loBase, uint32_t hiBase,
     }
 }
 
-// (a template only so that the header can be included by several translation units)
-template <int kInstance = 0>
+// GAPS: gap-score set compiled in as instruction immediates (s16_gap_set in kernels_s16.cuh; 0 = run-time values)
+template <int GAPS = 0>
 __global__ void __launch_bounds__(kLongMaxWarps * 32, 1) sw_s16_long_kernel(const S16LongParams prm) {
     constexpr int R = kLongR;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kLongMaxWarps * 32, 1) sw_s16_long_kernel(cons
     const uint32_t fifoOut = fifoIn + kLongFifoRows * 8;  // the next warp's input (unused by the last warp)
     uint2* border = prm.border + (size_t)blockIdx.x * prm.borderStride;
     const uint32_t NEG2 = ((uint32_t)(uint16_t)kNegS16 << 16) | (uint16_t)kNegS16;
+    const uint32_t gop2 = GAPS > 0 ? s16_gap_set(GAPS).x : prm.gop2, gex2 = GAPS > 0 ? s16_gap_set(GAPS).y : prm.gex2;
 
     // rows "before time 0" and between two periods are gap rows: the ring starts out as -16000 everywhere
     for (int i = threadIdx.x; i < 21 * rowWords; i += blockDim.x) {
@@ -279,9 +280,9 @@ __global__ void __launch_bounds__(kLongMaxWarps * 32, 1) sw_s16_long_kernel(cons
                         if (j + 1 < R) dNext = __vadd2(__vadd2(Hp[j], n0), n1);
                         const uint32_t h = __vimax3_s16x2_relu(d, E, F[j]);
                         Hp[j] = h;
-                        const uint32_t tt = __vadd2(h, prm.gop2);
-                        E = __viaddmax_s16x2(E, prm.gex2, tt);
-                        F[j] = __viaddmax_s16x2(F[j], prm.gex2, tt);
+                        const uint32_t tt = __vadd2(h, gop2);
+                        E = __viaddmax_s16x2(E, gex2, tt);
+                        F[j] = __viaddmax_s16x2(F[j], gex2, tt);
                         if (j & 1) mx = __vimax3_s16x2(mx, d, dPrev);
                         dPrev = d;
                         d = dNext;

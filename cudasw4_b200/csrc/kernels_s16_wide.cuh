@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_wide_kernel(const S16Wi
 #pragma unroll
                     for (int j = 0; j < R; j++) { Hp[j] = 0; F[j] = NEG2; }
                     HinPrev = 0;
+                    Elast = NEG2;  // hand-over registers start from the boundary values as well (see kernels_s16.cuh)
                     __syncwarp(groupMask);
                     fetch_lookahead(segsLeft > 0, laBlk);
                 }
@@ -247,8 +248,8 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_wide_kernel(const S16Wi
             // branch => no register shuffling at a merge point) on profile entries of -16000, with the hand-over
             // inputs forced to the boundary values so that nothing leaks into the freshly reset state; they can
             // never raise the running maximum.
-            const bool realRow = (unsigned)p < (unsigned)prm.qlen;
             if constexpr (MULTI) {
+                const bool realRow = (unsigned)p < (unsigned)prm.qlen;
                 // left border of a continued item: 32 rows at a time, coalesced; lane 0 is at row p
                 const int p0 = __shfl_sync(0xffffffffu, p, 0);
                 if ((p0 & 31) == 0 && p0 < prm.qlen) inBuf = useBorder ? border[p0 + lane] : make_uint2(0, NEG2);
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_wide_kernel(const S16Wi
                 if (m == 0) { Hin = bH; Ein = bE; }
                 if (!realRow) { Hin = 0; Ein = NEG2; }
             } else {
-                if (m == 0 || !realRow) { Hin = 0; Ein = NEG2; }
+                if (m == 0) { Hin = 0; Ein = NEG2; }  // gap rows need no forcing: every lane's state is reset at the restart
             }
             {
                 uint32_t E = Ein;

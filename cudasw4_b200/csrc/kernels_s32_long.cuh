@@ -45,8 +45,8 @@ __device__ __forceinline__ void long_ring_fill_s32(uint32_t base, int rowWords, 
     }
 }
 
-// (a template only so that the header can be included by several translation units)
-template <int kInstance = 0>
+// GAPS: gap-score set compiled in as instruction immediates (s16_gap_set in kernels_s16.cuh; 0 = run-time values)
+template <int GAPS = 0>
 __global__ void __launch_bounds__(kLongMaxWarps * 32, 1) sw_s32_long_kernel(const S32LongParams prm) {
     constexpr int R = kLongR;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(kLongMaxWarps * 32, 1) sw_s32_long_kernel(cons
     const uint32_t fifoIn = fifoBase + w * (kLongFifoRows * 8);
     const uint32_t fifoOut = fifoIn + kLongFifoRows * 8;
     int2* border = prm.border + (size_t)blockIdx.x * prm.borderStride;
-    const int gop = prm.gop, gex = prm.gex;
+    const int gop = GAPS > 0 ? (int)(short)(s16_gap_set(GAPS).x & 0xffffu) : prm.gop;
+    const int gex = GAPS > 0 ? (int)(short)(s16_gap_set(GAPS).y & 0xffffu) : prm.gex;
 
     for (int i = threadIdx.x; i < 21 * rowWords; i += blockDim.x) reinterpret_cast<int*>(smem)[i] = kNegS32;
     __syncthreads();

@@ -14,6 +14,8 @@ namespace sw4 {
 
 // two-rows-per-step kernel, subjects <= 512 (R = 4, 6, ..., 32); cudaErrorInvalidValue for an unknown R
 cudaError_t launch_s16(int R, const S16Params& prm, int grid, cudaStream_t stream);
+// the same kernel in its multi-segment form (items of several 16 x R-column segments, R = 18..32)
+cudaError_t launch_s16_multi(int R, const S16Params& prm, int grid, cudaStream_t stream);
 // full-warp one-row-per-step kernel, 513..1024 (R = 18..32) and the multi-segment class (R = 32, multi)
 cudaError_t launch_s16_wide(int R, bool multi, const S16WideParams& prm, int grid, cudaStream_t stream);
 // CTA-wide systolic arrays for long subjects (blockDim = 32 * prm.warps)

@@ -5,20 +5,32 @@
 
 namespace sw4 {
 
-cudaError_t launch_s16_long(const S16LongParams& prm, int grid, cudaStream_t stream) {
+template <int GAPS>
+static cudaError_t launch_s16_long_gaps(const S16LongParams& prm, int grid, cudaStream_t stream) {
     static bool configured[64] = {};
-    cudaError_t e = ensure_smem_attr(sw_s16_long_kernel<0>, s16_long_smem_bytes(kLongMaxWarps), configured);
+    cudaError_t e = ensure_smem_attr(sw_s16_long_kernel<GAPS>, s16_long_smem_bytes(kLongMaxWarps), configured);
     if (e != cudaSuccess) return e;
-    sw_s16_long_kernel<0><<<grid, prm.warps * 32, s16_long_smem_bytes(prm.warps), stream>>>(prm);
+    sw_s16_long_kernel<GAPS><<<grid, prm.warps * 32, s16_long_smem_bytes(prm.warps), stream>>>(prm);
     return cudaGetLastError();
 }
+cudaError_t launch_s16_long(const S16LongParams& prm, int grid, cudaStream_t stream) {
+    static const bool generic = getenv("SW4_NO_GAP_SETS") != nullptr;
+    if (!generic && s16_gap_set_for(prm.gop2, prm.gex2) == 1) return launch_s16_long_gaps<1>(prm, grid, stream);
+    return launch_s16_long_gaps<0>(prm, grid, stream);
+}
 
-cudaError_t launch_s32_long(const S32LongParams& prm, int grid, cudaStream_t stream) {
+template <int GAPS>
+static cudaError_t launch_s32_long_gaps(const S32LongParams& prm, int grid, cudaStream_t stream) {
     static bool configured[64] = {};
-    cudaError_t e = ensure_smem_attr(sw_s32_long_kernel<0>, s32_long_smem_bytes(kLongMaxWarps), configured);
+    cudaError_t e = ensure_smem_attr(sw_s32_long_kernel<GAPS>, s32_long_smem_bytes(kLongMaxWarps), configured);
     if (e != cudaSuccess) return e;
-    sw_s32_long_kernel<0><<<grid, prm.warps * 32, s32_long_smem_bytes(prm.warps), stream>>>(prm);
+    sw_s32_long_kernel<GAPS><<<grid, prm.warps * 32, s32_long_smem_bytes(prm.warps), stream>>>(prm);
     return cudaGetLastError();
+}
+cudaError_t launch_s32_long(const S32LongParams& prm, int grid, cudaStream_t stream) {
+    static const bool generic = getenv("SW4_NO_GAP_SETS") != nullptr;
+    if (!generic && prm.gop == -11 && prm.gex == -1) return launch_s32_long_gaps<1>(prm, grid, stream);
+    return launch_s32_long_gaps<0>(prm, grid, stream);
 }
 
 cudaError_t launch_s32(const S32Params& prm, int blocks, cudaStream_t stream) {

@@ -1,18 +1,26 @@
-// Instantiations + launcher of the two-rows-per-step packed kernel (kernels_s16.cuh), one per length class.
+// Instantiations + launcher of the two-rows-per-step packed kernel (kernels_s16.cuh), one per length class and gap set.
+// SW4_GAPS selects the gap-score set this translation unit instantiates (one unit per set so that they build in parallel).
 #include <cstdlib>
 #include "launch.hpp"
+
+#ifndef SW4_GAPS
+#define SW4_GAPS 0
+#endif
 
 namespace sw4 {
 
 template <int R>
 static cudaError_t launch_one(const S16Params& prm, int grid, cudaStream_t stream) {
     static bool configured[64] = {};
-    cudaError_t e = ensure_smem_attr(sw_s16_kernel<R>, s16_smem_bytes<R>(), configured);
+    auto kernel = sw_s16_kernel<R, false, SW4_GAPS>;
+    cudaError_t e = ensure_smem_attr(kernel, s16_smem_bytes<R>(), configured);
     if (e != cudaSuccess) return e;
-    return launch_clustered(sw_s16_kernel<R>, prm, grid, kS16Threads, s16_smem_bytes<R>(), stream);
+    return launch_clustered(kernel, prm, grid, kS16Threads, s16_smem_bytes<R>(), stream);
 }
 
-cudaError_t launch_s16(int R, const S16Params& prm, int grid, cudaStream_t stream) {
+#define SW4_CAT2(a, b) a##b
+#define SW4_CAT(a, b) SW4_CAT2(a, b)
+cudaError_t SW4_CAT(launch_s16_gaps, SW4_GAPS)(int R, const S16Params& prm, int grid, cudaStream_t stream) {
     switch (R) {
         case 4: return launch_one<4>(prm, grid, stream);
         case 6: return launch_one<6>(prm, grid, stream);
@@ -32,5 +40,21 @@ cudaError_t launch_s16(int R, const S16Params& prm, int grid, cudaStream_t strea
         default: return cudaErrorInvalidValue;
     }
 }
+
+#if SW4_GAPS == 0
+cudaError_t launch_s16_gaps1(int R, const S16Params& prm, int grid, cudaStream_t stream);
+cudaError_t launch_s16_gaps2(int R, const S16Params& prm, int grid, cudaStream_t stream);
+cudaError_t launch_s16_gaps3(int R, const S16Params& prm, int grid, cudaStream_t stream);
+// picks the instantiation whose immediates equal the requested gap scores, else the run-time one
+cudaError_t launch_s16(int R, const S16Params& prm, int grid, cudaStream_t stream) {
+    static const bool generic = getenv("SW4_NO_GAP_SETS") != nullptr;
+    switch (generic ? 0 : s16_gap_set_for(prm.gop2, prm.gex2)) {
+        case 1: return launch_s16_gaps1(R, prm, grid, stream);
+        case 2: return launch_s16_gaps2(R, prm, grid, stream);
+        case 3: return launch_s16_gaps3(R, prm, grid, stream);
+        default: return launch_s16_gaps0(R, prm, grid, stream);
+    }
+}
+#endif
 
 }  // namespace sw4
