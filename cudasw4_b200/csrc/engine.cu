@@ -776,6 +776,8 @@ struct Engine {
             ctx.borderSlots = needBorder ? (int)std::min<size_t>((size_t)sh.smCount, rows * 2 / 3 / groupsPerCta) : 0;
             ctx.borderRowArrays = rows - (size_t)ctx.borderSlots * groupsPerCta;
             ctx.dBorder.ensure(rows * ctx.borderStride);
+            // test hook: border rows full of large positive scores make any read of a stale entry show up in the results
+            if (getenv("SW4_DEBUG_POISON_BORDER")) SW4_CUDA(cudaMemset(ctx.dBorder.p, 0x7f, ctx.dBorder.bytes()));
             ctx.borderB = ctx.dBorder.p + (size_t)ctx.borderSlots * groupsPerCta * ctx.borderStride;
             ctx.dBorderSlots.ensure((size_t)std::max(ctx.borderSlots, 1));
         }

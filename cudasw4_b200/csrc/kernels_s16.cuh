@@ -428,8 +428,11 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
             const int plNext = (pl + kBatchSteps >= P) ? 0 : pl + kBatchSteps;
             const bool ub = (plNext == 0) ? nextUseBorder : useBorder;
             if (m < kBatchSteps) {
+                // Entries of steps beyond the query are never taken from memory: the last lane only ever stores entries
+                // up to P - 16 and whatever older scans (longer queries, other items) left behind there is not bounded by
+                // this item's scores - as input of the first lane's gap rows it could leak into the running maximum.
                 const uint32_t dst = bstage + ((batch + 1) & 1) * (kBatchSteps * 16) + m * 16;
-                if (ub) cp_async16(dst, borderBase + plNext + m);
+                if (ub && 2 * (plNext + m) < prm.qlen) cp_async16(dst, borderBase + plNext + m);
                 else sts_u128(dst, 0, NEG2, 0, NEG2);
             }
             cp_async_commit();
@@ -450,7 +453,9 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
             EinA = EinA * notFirst + negIfFirst; EinB = EinB * notFirst + negIfFirst;
 #else
             if constexpr (MULTI) {
-                const uint4 bv = lds_u128_imm<i * 16>(bstageRd);  // left border of this step's two rows (group broadcast)
+                // left border of this step's two rows (a group-wide broadcast load: predicating it on the first lane costs
+                // registers - more spills in the R >= 28 instantiations - for nothing measurable)
+                const uint4 bv = lds_u128_imm<i * 16>(bstageRd);
                 if (m == 0) { HinA = bv.x; EinA = bv.y; HinB = bv.z; EinB = bv.w; }
             } else {
                 if (m == 0) { HinA = 0; EinA = NEG2; HinB = 0; EinB = NEG2; }

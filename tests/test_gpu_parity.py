@@ -614,3 +614,37 @@ def test_pseudo_database_with_lengths_is_reproducible(oracle):
     s, i = oracle.topk(ref, 10)
     assert [m[0] for m in merged[:10]] == s.tolist() and [m[1] for m in merged[:10]] == i.tolist()
     assert merged[0][1] == gid
+
+
+def test_border_rows_never_leak_stale_entries(oracle):
+    """The border scratch of the long-subject kernels is reused across items, segments, queries and scans. With the
+    buffer poisoned (SW4_DEBUG_POISON_BORDER: every entry a large positive score) any read of an entry the current
+    alignment did not write itself would raise a score. Run in a subprocess (the switch is read by the library)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import cudasw4_b200 as sw
+from cudasw4_b200 import dbformat, synth
+from tests import oracle_lib
+oracle = oracle_lib.load()
+rng = np.random.default_rng(12)
+L = np.concatenate([rng.integers(513, 1025, 900), rng.integers(1025, 6000, 500), rng.integers(20, 512, 300)])
+db = dbformat.from_sequences([synth.random_residues(rng, int(n)) for n in L])
+with sw.CudaSW4(deviceIds=[0], numTop=10, blosumType=62) as eng:
+    eng.setDatabase(db)
+    for ql in (3001, 97, 640, 1530, 33):
+        q = synth.random_residues(rng, ql)
+        res = eng.scan(dbformat.decode(q))
+        scores, ids = eng.lastScanAllScores()
+        got = np.empty(db.num_sequences, np.int32); got[ids] = scores
+        ref = oracle.scan(62, q, db, -11, -1)
+        bad = np.nonzero(got != ref)[0]
+        assert len(bad) == 0, (ql, bad[:8], got[bad[:8]], ref[bad[:8]], db.lengths[bad[:8]])
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in ({}, {"SW4_LONG_ARRAY_ITEMS_PER_GROUP": "0"}, {"SW4_NO_TWO_ROW_MULTI": "1"}):
+        env = dict(os.environ, SW4_DEBUG_POISON_BORDER="1", **extra)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "ok" in r.stdout, (extra, r.stdout[-500:], r.stderr[-1500:])
