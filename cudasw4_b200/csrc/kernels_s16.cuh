@@ -145,10 +145,43 @@ __host__ __device__ constexpr int s16_prefetch_depth() {
 #endif
 }
 
+// The same refill with everything that does not change from batch to batch precomputed once per thread and parked in
+// shared memory (round 2; ptxas re-derives such values from the thread index every batch rather than spend two
+// registers on them, ~60 instructions per thread and batch): thread t copies the 16-byte piece c = t & 3 of the rows
+// f = (t >> 2) + 128 k, k = 0..3. plan[t] = (ring byte address of slot 0 of row f0 / piece c, byte offset of the same
+// piece at position 0 inside the profile).
+constexpr int kFillPlanBytes = kS16Threads * 8;
+__device__ __forceinline__ void ring_fill_plan(uint32_t planBase, uint32_t ringBase, int profStride) {
+    const int f0 = threadIdx.x >> 2, c = threadIdx.x & 3;
+    const uint32_t dst0 = ringBase + (f0 * kRingStride + 32 + 4 * c) * 4;
+    const uint32_t srcOff0 = ((uint32_t)f0 * (uint32_t)profStride + 4u * c) * 4u;
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(planBase + threadIdx.x * 8), "r"(dst0), "r"(srcOff0) : "memory");
+}
+__device__ __forceinline__ void ring_fill_fast(uint32_t planBase, const uint32_t* __restrict__ profile, int profStride, int x0, int p0) {
+    static_assert(kS16Threads == 512, "the plan covers 441 rows x 4 pieces with 512 threads in 4 rounds");
+    uint32_t dst, srcOff;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(dst), "=r"(srcOff) : "r"(planBase + threadIdx.x * 8));
+    const int slot0 = x0 & (kRingSlots - 1);
+    const bool mirror = slot0 >= 32;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(profile) + (srcOff + (uint32_t)p0 * 4u);
+    const uint32_t rowStep = 128u * (uint32_t)profStride * 4u;
+    dst += slot0 * 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (k < 3 || threadIdx.x < (kFused - 384) * 4) {
+            cp_async16(dst + k * (128 * kRingStride * 4), src);
+            if (mirror) cp_async16(dst + k * (128 * kRingStride * 4) - kRingSlots * 4, src);
+        }
+        src += rowStep;
+    }
+    cp_async_commit();
+}
+
 constexpr int kBorderStageBytes = 2 * kBatchSteps * 16;  // per group: two batches of (H_a, E_a, H_b, E_b) per step
 template <int R, bool MULTI = false>
-constexpr int s16_smem_bytes() {
-    return kRingBytes + kS16Warps * 32 * R * 2 + kS16Warps * 4 * kGroupStateInts * 4 + (MULTI ? kS16Warps * 2 * kBorderStageBytes : 0);
+__host__ __device__ constexpr int s16_smem_bytes() {
+    return kRingBytes + kS16Warps * 32 * R * 2 + kS16Warps * 4 * kGroupStateInts * 4 + (MULTI ? kS16Warps * 2 * kBorderStageBytes : 0) +
+           kS16Threads * 8;  // ... + the refill plan (ring_fill_plan)
 }
 
 // Refill the ring slots of query rows [x0, x0+16) (x0 % 16 == 0); p0 = x0 mod periodRows (periodRows % 16 == 0).
@@ -330,7 +363,10 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
     // slots must read as gap rows too, so the whole ring starts out as -16000; then the first batch + first pair-blocks.
     for (int i = threadIdx.x; i < kFused * kRingStride; i += kS16Threads) reinterpret_cast<uint32_t*>(smem)[i] = NEG2;
     __syncthreads();
-    ring_fill(ringBase, prm.profile, prm.profStride, 0, 0);
+    constexpr int kSmemBytes = s16_smem_bytes<R, MULTI>();
+    const uint32_t fillPlan = ringBase + kSmemBytes - kFillPlanBytes;
+    ring_fill_plan(fillPlan, ringBase, prm.profStride);
+    ring_fill_fast(fillPlan, prm.profile, prm.profStride, 0, 0);
     fetch_lookahead(false, 0);
     int pfill = kBatchRows % periodRows;  // (first row of the next fill) mod periodRows
     if constexpr (MULTI) {  // both staging buffers start out as the boundary column (H = 0, E = -inf)
@@ -343,7 +379,7 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
     for (int batch = 0;; ++batch) {
         cp_async_wait_all();
         if (!__syncthreads_or(alive)) break;
-        ring_fill(ringBase, prm.profile, prm.profStride, (batch + 1) * kBatchRows, pfill);
+        ring_fill_fast(fillPlan, prm.profile, prm.profStride, (batch + 1) * kBatchRows, pfill);
         pfill += kBatchRows;
         if (pfill >= periodRows) pfill -= periodRows;
         if (batch > 0) {
