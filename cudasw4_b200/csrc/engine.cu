@@ -568,7 +568,7 @@ struct Engine {
             sh.batches.push_back(makeBatch(sh, 0, n));
         } else {
             sh.streaming = true;
-            if (budget <= perSubject + ((size_t)2 << 20))
+            if (budget <= perSubject + ((size_t)64 << 10))
                 fail(SW4_ERR_NOMEM, "device %d: %zu MiB usable for the database (max_gpu_mem), the per-sequence arrays alone need %zu MiB",
                      sh.device, budget >> 20, perSubject >> 20);
             const size_t slotBytes = (budget - perSubject) / 2;

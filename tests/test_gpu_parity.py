@@ -648,3 +648,18 @@ print("ok")
         env = dict(os.environ, SW4_DEBUG_POISON_BORDER="1", **extra)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "ok" in r.stdout, (extra, r.stdout[-500:], r.stderr[-1500:])
+
+
+def test_benchmark_mode_without_result_lists(oracle):
+    """`--top 0` (the reference's benchmark mode, runpeakbenchmark.sh:27): scans run, nothing is selected or returned."""
+    db, rng = _mixed_db(5, 800, 20, 700)
+    qs = [dbformat.decode(synth.random_residues(rng, n)) for n in (50, 300)]
+    with _engine(numTop=0, blosumType=62) as eng:
+        eng.setDatabase(db)
+        res = eng.scan(qs[1])
+        assert res.scores == [] and res.referenceIds == [] and res.stats.gcups > 0
+        scores, ids = eng.lastScanAllScores()
+        ref = oracle.scan(62, dbformat.encode(qs[1]), db, -11, -1)
+        assert (scores == ref[ids]).all()
+        many, total = eng.scanMany(qs + [""])
+        assert [m.scores for m in many] == [[], [], []] and total.cells == sum(m.stats.cells for m in many)
