@@ -373,6 +373,7 @@ struct Engine {
     bool verbose = false;
     // development switches
     bool useLongKernel = [] { const char* e = getenv("SW4_NO_LONG_KERNEL"); return !e; }();
+    bool useLong2Kernel = [] { const char* e = getenv("SW4_NO_LONG2_KERNEL"); return !e; }();  // two rows per step
     int longMinWarps = [] { const char* e = getenv("SW4_LONG_MIN_WARPS"); return e ? std::max(2, atoi(e)) : 2; }();
     int backfillItems = [] { const char* e = getenv("SW4_BACKFILL_ITEMS"); return e ? std::max(1, atoi(e)) : 4; }();
     // classes above 512 columns: the multi-segment two-rows-per-step kernel (default) or the older full-warp one-row kernel
@@ -747,7 +748,7 @@ struct Engine {
             while (cap < qlen) cap *= 2;
             ctx.queryCapacity = cap;
             ctx.topCapacity = std::max(ctx.topCapacity, (size_t)std::max(k, 64));
-            const size_t capStride = (size_t)(cap + 64 + 31) / 32 * 32;
+            const size_t capStride = (size_t)(cap + 96 + 31) / 32 * 32;
             ctx.dQueryLetters.ensure((size_t)cap + 16);
             ctx.dQueryCodes.ensure((size_t)cap + 16);
             ctx.dProfile.ensure((size_t)kProfileRows * capStride);
@@ -795,7 +796,7 @@ struct Engine {
         const int qpad = (qlen + 3) / 4 * 4;
         // rows of the positional profile start on 128-byte lines: the ring refill copies 64 contiguous bytes per row, which
         // then always fall into two sectors of one line (a stride of 4 mod 8 words cost 3-4 % on the peak benchmark)
-        ctx.profStride = (qlen + 64 + 31) / 32 * 32;
+        ctx.profStride = (qlen + 96 + 31) / 32 * 32;  // (the two-row array kernel reads up to q + 80 gap rows)
         if (qlen) memcpy(ctx.hQuery.p, q.letters, (size_t)qlen);
         cudaStream_t st = ctx.stream;
         SW4_CUDA(cudaEventRecord(ctx.evStart, st));
@@ -888,6 +889,41 @@ struct Engine {
                     while (longWarps > 1 && kLongLag * longWarps + 64 > p0) longWarps >>= 1;
                     if (longWarps < longMinWarps) longWarps = 0;
                     if (longWarps && twoRowMulti && cl.numItems > longArrayMaxItemsPerGroup * sh.smCount * kS16Warps * 2) longWarps = 0;
+                }
+                int long2Period = 0;
+                const int long2Warps = (longWarps && useLong2Kernel) ? s16_long2_warps(qlen, &long2Period) : 0;
+                if (long2Warps) {  // the array kernel at two query rows per step (kernels_s16_long2.cuh)
+                    S16Long2Params lp{};
+                    lp.cols = cols;
+                    lp.items = items;
+                    lp.lengths = sh.dLengths.p;
+                    lp.numItems = cl.numItems;
+                    lp.ticket = ctx.dCounters.p + 8 + cl.cls;
+                    lp.warps = long2Warps;
+                    lp.ringSlots = s16_long2_ring_slots(long2Warps);
+                    lp.profLo = ctx.dProfile.p + (size_t)kFused * profStride;
+                    lp.profHi = ctx.dProfile.p + (size_t)(kFused + 21) * profStride;
+                    lp.profStride = profStride;
+                    lp.qlen = qlen;
+                    lp.period = long2Period;
+                    lp.gop2 = gop2;
+                    lp.gex2 = gex2;
+                    lp.ovfThreshold = kS16OverflowThreshold;
+                    lp.statThreshold = statThreshold();
+                    lp.scores = ctx.dScores.p;
+                    lp.ovfList = ctx.dOvfList.p;
+                    lp.ovfCount = ctx.dCounters.p + 0;
+                    lp.statCount = ctx.dCounters.p + 1;
+                    lp.border = reinterpret_cast<uint4*>(ctx.borderB);
+                    lp.borderStride = (int)(ctx.borderStride / 2);
+                    const int arrays = kLong2Warps / long2Warps;
+                    int g = std::max(1, std::min(sh.smCount, (cl.numItems + arrays - 1) / arrays));
+                    g = std::max(1, (int)std::min<size_t>((size_t)g, ctx.borderRowArrays / arrays));
+                    SW4_CUDA(launch_s16_long2(lp, g, cst));
+                    ctx.launches++;
+                    SW4_CUDA(cudaEventRecord(ctx.evJoin[ci % kMaxClassStreams], cst));
+                    SW4_CUDA(cudaStreamWaitEvent(st, ctx.evJoin[ci % kMaxClassStreams], 0));
+                    continue;
                 }
                 if (longWarps) {
                     S16LongParams lp{};

@@ -7,6 +7,7 @@
 #include "kernels_s16.cuh"
 #include "kernels_s16_wide.cuh"
 #include "kernels_s16_long.cuh"
+#include "kernels_s16_long2.cuh"
 #include "kernels_s32.cuh"
 #include "kernels_s32_long.cuh"
 
@@ -21,6 +22,8 @@ cudaError_t launch_s16_wide(int R, bool multi, const S16WideParams& prm, int gri
 // CTA-wide systolic arrays for long subjects (blockDim = 32 * prm.warps)
 cudaError_t launch_s16_long(const S16LongParams& prm, int grid, cudaStream_t stream);
 cudaError_t launch_s32_long(const S32LongParams& prm, int grid, cudaStream_t stream);
+// the same arrays at two query rows per step (16 / prm.warps arrays of prm.warps warps per 512-thread CTA)
+cudaError_t launch_s16_long2(const S16Long2Params& prm, int grid, cudaStream_t stream);
 // exact 32-bit wavefront, one subject per warp
 cudaError_t launch_s32(const S32Params& prm, int blocks, cudaStream_t stream);
 

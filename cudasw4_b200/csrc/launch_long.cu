@@ -20,6 +20,20 @@ cudaError_t launch_s16_long(const S16LongParams& prm, int grid, cudaStream_t str
 }
 
 template <int GAPS>
+static cudaError_t launch_s16_long2_gaps(const S16Long2Params& prm, int grid, cudaStream_t stream) {
+    static bool configured[64] = {};
+    cudaError_t e = ensure_smem_attr(sw_s16_long2_kernel<GAPS>, s16_long2_smem_bytes(kLong2MaxW), configured);
+    if (e != cudaSuccess) return e;
+    sw_s16_long2_kernel<GAPS><<<grid, kLong2Warps * 32, s16_long2_smem_bytes(prm.warps), stream>>>(prm);
+    return cudaGetLastError();
+}
+cudaError_t launch_s16_long2(const S16Long2Params& prm, int grid, cudaStream_t stream) {
+    static const bool generic = getenv("SW4_NO_GAP_SETS") != nullptr;
+    if (!generic && s16_gap_set_for(prm.gop2, prm.gex2) == 1) return launch_s16_long2_gaps<1>(prm, grid, stream);
+    return launch_s16_long2_gaps<0>(prm, grid, stream);
+}
+
+template <int GAPS>
 static cudaError_t launch_s32_long_gaps(const S32LongParams& prm, int grid, cudaStream_t stream) {
     static bool configured[64] = {};
     cudaError_t e = ensure_smem_attr(sw_s32_long_kernel<GAPS>, s32_long_smem_bytes(kLongMaxWarps), configured);
