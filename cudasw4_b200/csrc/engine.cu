@@ -890,9 +890,16 @@ struct Engine {
                     if (longWarps < longMinWarps) longWarps = 0;
                     if (longWarps && twoRowMulti && cl.numItems > longArrayMaxItemsPerGroup * sh.smCount * kS16Warps * 2) longWarps = 0;
                 }
+                // The two-rows-per-step form of the array kernel (kernels_s16_long2.cuh) has 20 % fewer instructions per cell but
+                // fits at most 8 warps - and only half as many as the one-row form at a given query length - into an array.
+                // It wins whenever that does not cost array width (measured on C5, per query: +9..+12 % at W = 8 vs 8 or 16,
+                // +9 % at 4 vs 4; -28 % at 4 vs 8, -43 % at 2 vs 4), unless there are too few items to keep its 2 x 148
+                // arrays of 8 warps busy (then the 16-warp array finishes the few long alignments sooner).
                 int long2Period = 0;
-                const int long2Warps = (longWarps && useLong2Kernel) ? s16_long2_warps(qlen, &long2Period) : 0;
-                if (long2Warps) {  // the array kernel at two query rows per step (kernels_s16_long2.cuh)
+                int long2Warps = (longWarps && useLong2Kernel) ? s16_long2_warps(qlen, &long2Period) : 0;
+                if (long2Warps < std::min(longWarps, kLong2MaxW) || qlen < 256) long2Warps = 0;
+                if (long2Warps && longWarps > kLong2MaxW && cl.numItems < 2 * sh.smCount) long2Warps = 0;
+                if (long2Warps) {
                     S16Long2Params lp{};
                     lp.cols = cols;
                     lp.items = items;

@@ -21,7 +21,9 @@
 namespace sw4 {
 
 constexpr int kLag2 = 40;            // steps between consecutive warps of an array
-constexpr int kFifo2 = 16;           // entries (steps) per warp FIFO; an entry is consumed 9 steps after it was produced
+constexpr int kFifo2 = 32;           // entries (steps) per warp FIFO: an entry is consumed 9 steps after it was produced and its
+                                     // slot rewritten 32 steps after that - always at least one CTA barrier later (with 16 entries
+                                     // the rewrite could fall into the very batch of the read: racecheck found it)
 constexpr int kLong2Warps = 16;      // warps per CTA (16 / W arrays of W warps)
 constexpr int kLong2MaxW = 8;
 
@@ -37,7 +39,7 @@ struct S16Long2Params {
     const uint32_t* profHi;      // [21][profStride]  (M[q_p][s] << 16),   rows p >= qlen hold 0xc1800000
     int profStride;              // >= 2 * period
     int qlen;
-    int period;                  // P in STEPS: multiple of 8, >= ceil(q/2) + 32 and >= 40 W + 16
+    int period;                  // P in STEPS: multiple of 16, >= ceil(q/2) + 32 and >= 40 W + 16
     uint32_t gop2, gex2;
     int ovfThreshold, statThreshold;
     int32_t* scores;             // must hold -1 (or any value below every score) for the class's subjects at launch
@@ -54,7 +56,7 @@ static inline int s16_long2_smem_bytes(int warps) {
 }
 // W for a query: the largest power of two <= 8 whose array fits the period; 0 = query too short for an array
 static inline int s16_long2_warps(int qlen, int* periodOut) {
-    const int p0 = ((qlen + 1) / 2 + 32 + 7) / 8 * 8;
+    const int p0 = ((qlen + 1) / 2 + 32 + 15) / 16 * 16;  // (entries of the last 32 steps of a period are gap steps: never read)
     int w = kLong2MaxW;
     while (w > 1 && kLag2 * w + 16 > p0) w >>= 1;
     if (periodOut) *periodOut = p0;
@@ -243,18 +245,34 @@ __global__ void __launch_bounds__(kLong2Warps * 32, 1) sw_s16_long2_kernel(const
         }
         if (p == pRestart && alive) restart();  // warp-uniform
         if (haveWork) {
+            // hand-over addresses of this batch, all in terms of the first lane's step p0 (a multiple of 8): lane 0 reads
+            // FIFO entry (p0 + i) & 31, lane 31 - 31 steps behind - writes entry (p0 - 31 + i) & 31; only its last step of a
+            // batch can cross a multiple of 32 or the end of the period
+            const int p0 = __shfl_sync(0xffffffffu, p, 0);
+            const uint32_t inBase = fifoIn + (p0 & (kFifo2 - 8)) * 16;
+            const int nReal = qSteps - p0;  // steps of this batch (counted from 0) that are real rows for the first lane
+            int p31 = p0 - 31;
+            if (p31 < 0) p31 += P;
+            int e7 = p31 + 7;
+            if (e7 >= P) e7 -= P;
+            const uint32_t outA = fifoOut + (p31 & (kFifo2 - 1)) * 16, out7 = fifoOut + (e7 & (kFifo2 - 1)) * 16;
+            uint4* const bA = border + p31;
+            uint4* const b7 = border + e7;
+            const bool first = lane == 0, last = lane == 31, lastWarp = w + 1 == W;
+            const bool take = first && useBorder;
             static_for<8>([&](auto stepIndex) {
                 constexpr int i = decltype(stepIndex)::value;
                 uint32_t HinA = __shfl_up_sync(0xffffffffu, HlastA, 1);
                 uint32_t EinA = __shfl_up_sync(0xffffffffu, ElastA, 1);
                 uint32_t HinB = __shfl_up_sync(0xffffffffu, Hp[R - 1], 1);
                 uint32_t EinB = __shfl_up_sync(0xffffffffu, ElastB, 1);
-                if (lane == 0) {
-                    // the block's left border: the FIFO (or the boundary column for an item's first block). Steps beyond the
-                    // query never read it: what lies there is not bounded by this block's scores.
-                    HinA = 0; EinA = NEG2; HinB = 0; EinB = NEG2;
-                    if (useBorder && p + i < qSteps) {
-                        const uint4 bv = lds_u128(fifoIn + ((p + i) & (kFifo2 - 1)) * 16);
+                if (first) {
+                    // the block's left border for lane 0: the FIFO entry of this step - or the boundary column for an item's
+                    // first block (the FIFO then holds another item's values) and for gap steps (their entries are not
+                    // bounded by this block's scores, and their slots may be in the middle of being rewritten)
+                    HinA = 0u; EinA = NEG2; HinB = 0u; EinB = NEG2;
+                    if (take && i < nReal) {
+                        const uint4 bv = lds_u128_imm<i * 16>(inBase);
                         HinA = bv.x; EinA = bv.y; HinB = bv.z; EinB = bv.w;
                     }
                 }
@@ -302,13 +320,9 @@ __global__ void __launch_bounds__(kLong2Warps * 32, 1) sw_s16_long2_kernel(const
                     ElastB = E2;
                     HinPrevB = HinB;
                 }
-                if (lane == 31) {  // right border of the block for this step's two rows
-                    int e = p + i;
-                    if (e >= P) e -= P;
-                    if (e < qSteps) {
-                        if (w + 1 < W) sts_u128(fifoOut + (e & (kFifo2 - 1)) * 16, HlastA, ElastA, Hp[R - 1], ElastB);
-                        else border[e] = make_uint4(HlastA, ElastA, Hp[R - 1], ElastB);
-                    }
+                if (last) {  // right border of the block for this step's two rows (gap steps included, see above)
+                    if (lastWarp) *(i < 7 ? bA + i : b7) = make_uint4(HlastA, ElastA, Hp[R - 1], ElastB);
+                    else sts_u128(i < 7 ? outA + i * 16 : out7, HlastA, ElastA, Hp[R - 1], ElastB);
                 }
             });
         }
