@@ -322,9 +322,6 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
     // step pRestart. Restarts can only fall on the first step of a batch (P and the group offsets are multiples of 8).
     int p = (hl == 0) ? 0 : P - hl;
     const int pRestart = (m == 0) ? 0 : P - m;
-#ifdef SW4_HANDOVER_IMAD
-    const uint32_t notFirst = (m != 0) ? 1u : 0u, negIfFirst = (m != 0) ? 0u : NEG2;
-#endif
     bool haveWork = false;    // a segment is being computed
     bool alive = (warp * groupsPerWarp + g) < prm.activeGroups;  // the group still has something to compute or start
 
@@ -484,10 +481,6 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
             uint32_t HinB = __shfl_up_sync(0xffffffffu, Hp[R - 1], 1);
             uint32_t EinB = __shfl_up_sync(0xffffffffu, ElastB, 1);
             // the first lane of a group takes the boundary column (H = 0, E = -inf) instead of its neighbour's values
-#ifdef SW4_HANDOVER_IMAD
-            HinA *= notFirst; HinB *= notFirst;                          // IMAD: FMA pipe instead of an ALU-pipe SEL
-            EinA = EinA * notFirst + negIfFirst; EinB = EinB * notFirst + negIfFirst;
-#else
             if constexpr (MULTI) {
                 // left border of this step's two rows (a group-wide broadcast load: predicating it on the first lane costs
                 // registers - more spills in the R >= 28 instantiations - for nothing measurable)
@@ -496,7 +489,6 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
             } else {
                 if (m == 0) { HinA = 0; EinA = NEG2; HinB = 0; EinB = NEG2; }
             }
-#endif
             {
                 uint32_t E1 = EinA, E2 = EinB;
                 // substitution words are fetched kPrefetch columns ahead of their use: an explicit software pipeline, because

@@ -10,7 +10,7 @@ timeout 300 python bench.py --impl reference --steps 1 --warmup 1 2>/dev/null | 
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$R.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-c4 --no-ref-gpu > gpurun_out/bench_under_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:sw_s16_kernel -s 3 -c 1 -f -o gpurun_out/prof_s16_$R python tools/ncu_target.py 1000000 256 12 1 2>&1 | tail -2
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:sw_s16_kernel -s 3 -c 1 -f -o gpurun_out/prof_s16_multi_$R python tools/ncu_target.py 200000 768 12 1 2>&1 | tail -2
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:sw_s16_long_kernel -s 3 -c 1 -f -o gpurun_out/prof_s16_long_$R python tools/ncu_long_target.py 2 2>&1 | tail -2
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sw_s16_long2_kernel -s 0 -c 1 -f -o gpurun_out/prof_s16_long_$R python tools/ncu_long_target.py 2 2>&1 | tail -2
 timeout 900 python tools/compare_reference.py c2 c2d c3 c5 2>&1 | tail -3
 cp gpurun_out/compare_reference.md gpurun_out/compare_reference_$R.md
 head -12 gpurun_out/compare_reference_$R.md
