@@ -663,3 +663,36 @@ def test_benchmark_mode_without_result_lists(oracle):
         assert (scores == ref[ids]).all()
         many, total = eng.scanMany(qs + [""])
         assert [m.scores for m in many] == [[], [], []] and total.cells == sum(m.stats.cells for m in many)
+
+
+def test_huge_query_and_tight_scratch(oracle):
+    """A 70,000-residue query (profile of 140 MB, periods of 35,000 steps, border rows of 0.5 MB each) and the same
+    database under a border-scratch budget so small that the multi-segment kernels get fewer slots than CTAs (they then
+    wait for one another) or none at all (fallback to the one-warp-per-pair kernel)."""
+    rng = np.random.default_rng(70)
+    L = np.concatenate([rng.integers(40, 1100, 260), rng.integers(1100, 4000, 40), [20000]])
+    seqs = [synth.random_residues(rng, int(n)) for n in L]
+    q = synth.random_residues(rng, 70000)
+    q[30000:30000 + len(seqs[270])] = seqs[270]  # one planted subject
+    db = dbformat.from_sequences(seqs)
+    ref = oracle.scan(62, q, db, -11, -1)
+    s, i = oracle.topk(ref, 10)
+    with _engine(numTop=10, blosumType=62) as eng:
+        eng.setDatabase(db)
+        res = eng.scan(dbformat.decode(q))
+        scores, ids = eng.lastScanAllScores()
+        assert (scores == ref[ids]).all(), np.nonzero(scores != ref[ids])[0][:8]
+        assert res.scores == s.tolist() and res.referenceIds == i.tolist()
+    q2 = q[29000:33000]
+    ref2 = oracle.scan(62, q2, db, -11, -1)
+    for temp in (24 << 20, 3 << 20):   # 4000-residue query: 33 KB per border row array
+        with _engine(numTop=10, blosumType=62, memoryConfig=sw.MemoryConfig(maxTempBytes=temp)) as eng:
+            eng.setDatabase(db)
+            for rep in range(2):
+                eng.scan(dbformat.decode(q2))
+                scores, ids = eng.lastScanAllScores()
+                assert (scores == ref2[ids]).all(), (temp, np.nonzero(scores != ref2[ids])[0][:8])
+    with _engine(numTop=10, blosumType=62, memoryConfig=sw.MemoryConfig(maxTempBytes=256 << 10)) as eng:
+        eng.setDatabase(db)
+        with pytest.raises(sw.SW4Error):   # not even 16 row arrays fit: refused up front, not mid-scan
+            eng.scan(dbformat.decode(q2))
