@@ -15,8 +15,12 @@ static cudaError_t launch_s16_long_gaps(const S16LongParams& prm, int grid, cuda
 }
 cudaError_t launch_s16_long(const S16LongParams& prm, int grid, cudaStream_t stream) {
     static const bool generic = getenv("SW4_NO_GAP_SETS") != nullptr;
-    if (!generic && s16_gap_set_for(prm.gop2, prm.gex2) == 1) return launch_s16_long_gaps<1>(prm, grid, stream);
-    return launch_s16_long_gaps<0>(prm, grid, stream);
+    switch (generic ? 0 : s16_gap_set_for(prm.gop2, prm.gex2)) {
+        case 1: return launch_s16_long_gaps<1>(prm, grid, stream);
+        case 2: return launch_s16_long_gaps<2>(prm, grid, stream);
+        case 3: return launch_s16_long_gaps<3>(prm, grid, stream);
+        default: return launch_s16_long_gaps<0>(prm, grid, stream);
+    }
 }
 
 template <int GAPS>
@@ -29,8 +33,12 @@ static cudaError_t launch_s16_long2_gaps(const S16Long2Params& prm, int grid, cu
 }
 cudaError_t launch_s16_long2(const S16Long2Params& prm, int grid, cudaStream_t stream) {
     static const bool generic = getenv("SW4_NO_GAP_SETS") != nullptr;
-    if (!generic && s16_gap_set_for(prm.gop2, prm.gex2) == 1) return launch_s16_long2_gaps<1>(prm, grid, stream);
-    return launch_s16_long2_gaps<0>(prm, grid, stream);
+    switch (generic ? 0 : s16_gap_set_for(prm.gop2, prm.gex2)) {
+        case 1: return launch_s16_long2_gaps<1>(prm, grid, stream);
+        case 2: return launch_s16_long2_gaps<2>(prm, grid, stream);
+        case 3: return launch_s16_long2_gaps<3>(prm, grid, stream);
+        default: return launch_s16_long2_gaps<0>(prm, grid, stream);
+    }
 }
 
 template <int GAPS>

@@ -37,10 +37,16 @@ cudaError_t SW4_CAT(launch_s16_multi_gaps, SW4_GAPS)(int R, const S16Params& prm
 
 #if SW4_GAPS == 0
 cudaError_t launch_s16_multi_gaps1(int R, const S16Params& prm, int grid, cudaStream_t stream);
+cudaError_t launch_s16_multi_gaps2(int R, const S16Params& prm, int grid, cudaStream_t stream);
+cudaError_t launch_s16_multi_gaps3(int R, const S16Params& prm, int grid, cudaStream_t stream);
 cudaError_t launch_s16_multi(int R, const S16Params& prm, int grid, cudaStream_t stream) {
     static const bool generic = getenv("SW4_NO_GAP_SETS") != nullptr;
-    if (!generic && s16_gap_set_for(prm.gop2, prm.gex2) == 1) return launch_s16_multi_gaps1(R, prm, grid, stream);
-    return launch_s16_multi_gaps0(R, prm, grid, stream);
+    switch (generic ? 0 : s16_gap_set_for(prm.gop2, prm.gex2)) {
+        case 1: return launch_s16_multi_gaps1(R, prm, grid, stream);
+        case 2: return launch_s16_multi_gaps2(R, prm, grid, stream);
+        case 3: return launch_s16_multi_gaps3(R, prm, grid, stream);
+        default: return launch_s16_multi_gaps0(R, prm, grid, stream);
+    }
 }
 #endif
 
