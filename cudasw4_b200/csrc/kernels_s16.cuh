@@ -158,19 +158,20 @@ __device__ __forceinline__ void ring_fill_plan(uint32_t planBase, uint32_t ringB
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(planBase + threadIdx.x * 8), "r"(dst0), "r"(srcOff0) : "memory");
 }
 __device__ __forceinline__ void ring_fill_fast(uint32_t planBase, const uint32_t* __restrict__ profile, int profStride, int x0, int p0) {
-    static_assert(kS16Threads == 512, "the plan covers 441 rows x 4 pieces with 512 threads in 4 rounds");
+    constexpr int kRowsPerRound = kS16Threads / 4;                             // fused-pair rows covered by one round of all threads
+    constexpr int kRounds = (kFused + kRowsPerRound - 1) / kRowsPerRound;      // 4 with 512 threads
     uint32_t dst, srcOff;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(dst), "=r"(srcOff) : "r"(planBase + threadIdx.x * 8));
     const int slot0 = x0 & (kRingSlots - 1);
     const bool mirror = slot0 >= 32;
     const unsigned char* src = reinterpret_cast<const unsigned char*>(profile) + (srcOff + (uint32_t)p0 * 4u);
-    const uint32_t rowStep = 128u * (uint32_t)profStride * 4u;
+    const uint32_t rowStep = (uint32_t)kRowsPerRound * (uint32_t)profStride * 4u;
     dst += slot0 * 4;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (k < 3 || threadIdx.x < (kFused - 384) * 4) {
-            cp_async16(dst + k * (128 * kRingStride * 4), src);
-            if (mirror) cp_async16(dst + k * (128 * kRingStride * 4) - kRingSlots * 4, src);
+    for (int k = 0; k < kRounds; k++) {
+        if (k < kRounds - 1 || threadIdx.x < (kFused - (kRounds - 1) * kRowsPerRound) * 4) {
+            cp_async16(dst + k * (kRowsPerRound * kRingStride * 4), src);
+            if (mirror) cp_async16(dst + k * (kRowsPerRound * kRingStride * 4) - kRingSlots * 4, src);
         }
         src += rowStep;
     }
