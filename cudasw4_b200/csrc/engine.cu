@@ -1309,6 +1309,9 @@ int sw4_create(const int* device_ids, int num_devices, int num_top, int blosum, 
     *out = nullptr;
     sw4_handle* h = nullptr;
     int rc = guarded(nullptr, [&] {
+        // the length classes (and the queries in flight) run on their own streams: give them their own hardware queues
+        // (only effective when this process has not initialised CUDA yet; never overrides the caller's setting)
+        setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
         if (e != cudaSuccess || count == 0)
@@ -1316,9 +1319,6 @@ int sw4_create(const int* device_ids, int num_devices, int num_top, int blosum, 
                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
         h = new sw4_handle();
         sw4::Engine& eng = h->eng;
-        // the length classes (and the queries in flight) run on their own streams: give them their own hardware queues
-        // (only effective when this process has not created its CUDA context yet)
-        setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
         if (device_ids && num_devices > 0) {
             for (int i = 0; i < num_devices; i++) {
                 if (device_ids[i] < 0 || device_ids[i] >= count) sw4::fail(SW4_ERR_INVALID, "invalid device id %d", device_ids[i]);
