@@ -998,6 +998,8 @@ struct Engine {
                 } else {
                     fillCommon(narrow);
                     narrow.period = s16Period(qlen, G);
+                    narrow.firstSubject = cl.first;
+                    narrow.numSubjects = cl.count;
                 }
                 auto launchClass = [&](int g, cudaStream_t strm, int ctaOffset) {
                     cudaError_t e;

@@ -65,8 +65,10 @@ struct S16Item {
 
 struct S16Params {
     const uint16_t* cols;        // [numBlocks][G*R] fused column codes, lane-major (lane m owns [m*R, m*R+R))
-    const S16Item* items;        // [numItems] in the order they should be started
+    const S16Item* items;        // [numItems] in the order they should be started (read by the MULTI instantiations only)
     int numItems;
+    int firstSubject, numSubjects;  // single-segment classes: item k = subjects (firstSubject + 2k, + 2k + 1), pair-block k -
+                                 // derived on the spot instead of two dependent global loads at every restart
     int* ticket;                 // zero-initialised work counter (items are handed out dynamically)
     int logG;                    // G = 1 << logG lanes per group, 8 or 16
     const uint32_t* profile;     // [441][profStride] positional query profile, rows >= qlen hold -16000
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
         } else {
             if (m == 0) item = atomicAdd(prm.ticket, 1);
             item = __shfl_sync(groupMask, item, leader);
-            if (item < prm.numItems) { blk = prm.items[item].firstBlock * (MULTI ? prm.blockScale : 1); isNew = 1; }
+            if (item < prm.numItems) { blk = MULTI ? prm.items[item].firstBlock * prm.blockScale : item; isNew = 1; }
         }
         if (m == 0) { gs[3] = blk >= 0; gs[4] = blk; gs[5] = isNew; gs[6] = item; }
         if constexpr (MULTI) nextUseBorder = blk >= 0 && !isNew;
@@ -415,7 +417,16 @@ __global__ void __launch_bounds__(kS16Threads, 1) sw_s16_kernel(const S16Params 
             if constexpr (MULTI) writeBorder = false;
             if (laValid) {
                 if (laNew) {
-                    const S16Item it = prm.items[gs[6]];
+                    S16Item it;
+                    if constexpr (MULTI) {
+                        it = prm.items[gs[6]];
+                    } else {
+                        const int k = gs[6];
+                        it.subject0 = prm.firstSubject + 2 * k;
+                        it.subject1 = (2 * k + 1 < prm.numSubjects) ? it.subject0 + 1 : -1;
+                        it.firstBlock = k;
+                        it.numSegments = 1;
+                    }
                     int nseg = it.numSegments;
                     if constexpr (MULTI) {
                         nseg *= prm.blockScale;
