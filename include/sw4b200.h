@@ -62,8 +62,10 @@ typedef struct sw4_stats {
 } sw4_stats;
 
 typedef struct sw4_db_info {
-    uint64_t num_sequences;
-    uint64_t num_residues;       /* sum of true lengths */
+    uint64_t num_sequences;      /* sequences of the whole database (also for a pre-sharded handle)              */
+    uint64_t num_residues;       /* sum of true lengths of the sequences this handle HOLDS (the whole database    *
+                                  * unless it was set with sw4_set_database_shard_memory / _pseudo_database_lengths; *
+                                  * the same goes for min/max_length and partition_counts)                        */
     int32_t min_length, max_length;
     uint64_t partition_counts[36]; /* sequences per reference length partition (src/length_partitions.hpp) */
     int32_t shard_rank, shard_world;
